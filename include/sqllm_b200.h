@@ -1,0 +1,179 @@
+/*
+ * sqllm_b200.h - C ABI of the B200-native (sm_100a) dense-and-sparse LUT GEMV library
+ *                (libsqllm_b200.so), a from-scratch replacement for the hot path of
+ *                SqueezeAILab/SqueezeLLM:  squeezellm/quant_cuda_kernel.cu + quant_cuda.cpp.
+ *
+ * Boundary.  The reference exposes this path as a pybind11 C++ module `quant_cuda` whose 12
+ * functions take torch::Tensor by value (squeezellm/quant_cuda.cpp:257-270) - there is no C ABI in
+ * the reference.  This header is the C ABI that module sits on in our build: plain device
+ * pointers, sizes and a stream; no torch types.  Each of the 12 entry points below replaces the
+ * reference launcher named in its comment (same argument meaning, same accumulate-into-`mul`
+ * contract); squeezellm_b200/csrc/quant_cuda_pybind.cpp is the thin torch::Tensor wrapper that
+ * re-exports them under the reference's Python names.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless said otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - calls are asynchronous; nothing is retained after the call returns except `workspace`
+ *     contents, which belong to the library between calls on the same stream;
+ *   - return value: 0 on success, a negative SQLLM_E* code otherwise; sqllm_last_error() gives a
+ *     thread-local human readable message.  (The reference performs no checks at all:
+ *     squeezellm/quant_cuda_kernel.cu has no TORCH_CHECK / cudaGetLastError - SURVEY.md 8(b).)
+ *   - shapes (reference: squeezellm/quant.py:48-95):
+ *       vec           fp32 [batch, in]            (batch = 1 for the non-batched entry points)
+ *       mat3 / mat4   int32 [in/32*bits, out]     packed indices, row-major
+ *       lookup_table  fp32 [out, 2^bits]
+ *       mul           fp32 [batch, out]           ACCUMULATED INTO (caller pre-fills zeros or bias)
+ *       rows          int32 [out+1]   CSR row pointers, row = output channel
+ *       cols          int32 [nnz]     input index of each non-zero
+ *       vals          fp32  [nnz]
+ *       full_rows     fp32 [in, topX] ; full_row_indices int32 [topX]  (output channel of column j)
+ *     `height` = in/32*bits (rows of mat), `width` = out, as in the reference launchers.
+ *   - requirements (checked, SQLLM_EINVAL otherwise): in % 64 == 0, out % 4 == 0, 16-byte aligned
+ *     mat / vec, 1 <= batch.  The reference silently requires in % 128 == 0 and out % 128 == 0.
+ */
+#ifndef SQLLM_B200_H
+#define SQLLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQLLM_OK 0
+#define SQLLM_EINVAL (-1)   /* bad argument (shape, alignment, null pointer) */
+#define SQLLM_ECUDA (-2)    /* a CUDA runtime call or launch failed */
+#define SQLLM_EWORKSPACE (-3) /* workspace missing or too small */
+
+#define SQLLM_ABI_VERSION 1
+
+int sqllm_abi_version(void);
+const char *sqllm_last_error(void);
+
+/* Number of SMs x resident CTAs the persistent kernels will use on the current device
+ * (informational; also used by bench.py to report the grid). */
+int sqllm_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Workspace.  Used only by the *_fused entry point (deterministic cross-CTA reduction).  Must be
+ * zero-filled once after allocation (cudaMemset); the library keeps it consistent afterwards.
+ * One workspace must not be used by two streams concurrently.
+ * ------------------------------------------------------------------------------------------- */
+size_t sqllm_workspace_bytes(int bits, int in_features, int out_features, int topX);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generic descriptor entry point (what all 12 wrappers below call).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sqllm_lutgemv_args {
+    int bits;                 /* 3 or 4 */
+    int in_features;          /* K */
+    int out_features;         /* N */
+    int batch;                /* rows of vec / mul */
+    const int32_t *qweight;   /* [K/32*bits, N] */
+    const float *lookup_table;/* [N, 2^bits] */
+    const float *vec;         /* [batch, K] fp32 */
+    float *mul;               /* [batch, N] fp32, accumulated into */
+    /* optional CSR outliers (rows == NULL -> none) */
+    const int32_t *rows;
+    const int32_t *cols;
+    const float *vals;
+    /* optional dense rows (full_rows == NULL or topX == 0 -> none) */
+    const float *full_rows;
+    const int32_t *full_row_indices;
+    int topX;
+} sqllm_lutgemv_args;
+
+int sqllm_lutgemv(const sqllm_lutgemv_args *args, void *stream);
+
+/* Fused module path behind QuantLinearLUT.forward (squeezellm/quant.py:211-312), batch-1 decode:
+ *   y[c] = bias[c] + LUT-GEMV + CSR + dense rows, written (not accumulated) as fp16 or fp32,
+ * from an fp16 or fp32 x, in ONE launch: replaces torch.zeros (quant.py:218), x.float() (:223,267),
+ * the 1-3 reference launches and y.to(dtype) (:311).  Deterministic (fixed summation order).
+ * x_is_half / y_is_half select the element type of x / y.  bias may be NULL. */
+int sqllm_lutgemv_fused(const sqllm_lutgemv_args *args, /* vec/mul members ignored */
+                        const void *x, int x_is_half, void *y, int y_is_half, const float *bias,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The reference's 12 launchers, one C entry point each.
+ * ------------------------------------------------------------------------------------------- */
+/* vecquant3matmul_nuq_perchannel_cuda  - squeezellm/quant_cuda_kernel.cu:132-154 */
+int sqllm_vecquant3matmul_nuq_perchannel(const float *vec, const int32_t *mat, float *mul,
+                                         const float *lookup_table, int height, int width, void *stream);
+/* vecquant4matmul_nuq_perchannel_cuda  - squeezellm/quant_cuda_kernel.cu:157-179 */
+int sqllm_vecquant4matmul_nuq_perchannel(const float *vec, const int32_t *mat, float *mul,
+                                         const float *lookup_table, int height, int width, void *stream);
+/* vecquant3matmul_nuq_perchannel_batched_cuda - :182-207 ; batch = vec.size(0), vec_height = vec.size(1) */
+int sqllm_vecquant3matmul_nuq_perchannel_batched(const float *vec, const int32_t *mat, float *mul,
+                                                 const float *lookup_table, int height, int width,
+                                                 int batch, int vec_height, void *stream);
+/* vecquant4matmul_nuq_perchannel_batched_cuda - :210-235 */
+int sqllm_vecquant4matmul_nuq_perchannel_batched(const float *vec, const int32_t *mat, float *mul,
+                                                 const float *lookup_table, int height, int width,
+                                                 int batch, int vec_height, void *stream);
+/* vecquant3matmul_spmv_nuq_perchannel_cuda - :238-282  (mat = CSR values, mat3 = packed weights) */
+int sqllm_vecquant3matmul_spmv_nuq_perchannel(const int32_t *rows, const int32_t *cols, const float *mat,
+                                              const float *vec, float *mul, int num_rows,
+                                              const int32_t *mat3, const float *lookup_table,
+                                              int height, int width, void *stream);
+/* vecquant4matmul_spmv_nuq_perchannel_cuda - :285-327 */
+int sqllm_vecquant4matmul_spmv_nuq_perchannel(const int32_t *rows, const int32_t *cols, const float *mat,
+                                              const float *vec, float *mul, int num_rows,
+                                              const int32_t *mat4, const float *lookup_table,
+                                              int height, int width, void *stream);
+/* vecquant3matmul_spmv_nuq_perchannel_batched_cuda - :331-381 */
+int sqllm_vecquant3matmul_spmv_nuq_perchannel_batched(const int32_t *rows, const int32_t *cols, const float *mat,
+                                                      const float *vec, float *mul, int num_rows,
+                                                      const int32_t *mat3, const float *lookup_table,
+                                                      int height, int width, int batch, int vec_height,
+                                                      void *stream);
+/* vecquant4matmul_spmv_nuq_perchannel_batched_cuda - :385-435 */
+int sqllm_vecquant4matmul_spmv_nuq_perchannel_batched(const int32_t *rows, const int32_t *cols, const float *mat,
+                                                      const float *vec, float *mul, int num_rows,
+                                                      const int32_t *mat4, const float *lookup_table,
+                                                      int height, int width, int batch, int vec_height,
+                                                      void *stream);
+/* vecquant3matmul_spmv_hybrid_nuq_perchannel_cuda - :439-507 ; full_rows is [fr_height=in, fr_width=topX] */
+int sqllm_vecquant3matmul_spmv_hybrid_nuq_perchannel(const int32_t *rows, const int32_t *cols, const float *mat,
+                                                     const float *vec, const float *full_rows,
+                                                     const int32_t *full_row_indices, float *mul, int num_rows,
+                                                     const int32_t *mat3, const float *lookup_table,
+                                                     int height, int width, int fr_height, int fr_width,
+                                                     void *stream);
+/* vecquant4matmul_spmv_hybrid_nuq_perchannel_cuda - :511-577 */
+int sqllm_vecquant4matmul_spmv_hybrid_nuq_perchannel(const int32_t *rows, const int32_t *cols, const float *mat,
+                                                     const float *vec, const float *full_rows,
+                                                     const int32_t *full_row_indices, float *mul, int num_rows,
+                                                     const int32_t *mat4, const float *lookup_table,
+                                                     int height, int width, int fr_height, int fr_width,
+                                                     void *stream);
+/* vecquant3matmul_spmv_hybrid_nuq_perchannel_batched_cuda - :580-657 */
+int sqllm_vecquant3matmul_spmv_hybrid_nuq_perchannel_batched(const int32_t *rows, const int32_t *cols,
+                                                             const float *mat, const float *vec,
+                                                             const float *full_rows,
+                                                             const int32_t *full_row_indices, float *mul,
+                                                             int num_rows, const int32_t *mat3,
+                                                             const float *lookup_table, int height, int width,
+                                                             int fr_height, int fr_width, int batch,
+                                                             int vec_height, void *stream);
+/* vecquant4matmul_spmv_hybrid_nuq_perchannel_batched_cuda - :660-738 */
+int sqllm_vecquant4matmul_spmv_hybrid_nuq_perchannel_batched(const int32_t *rows, const int32_t *cols,
+                                                             const float *mat, const float *vec,
+                                                             const float *full_rows,
+                                                             const int32_t *full_row_indices, float *mul,
+                                                             int num_rows, const int32_t *mat4,
+                                                             const float *lookup_table, int height, int width,
+                                                             int fr_height, int fr_width, int batch,
+                                                             int vec_height, void *stream);
+
+/* Test hook: unpack the packed indices on the GPU exactly as the GEMV kernels do
+ * (idx uint8 [in, out]); lets tests prove the integer path bit-exact on its own. */
+int sqllm_unpack_indices(int bits, const int32_t *qweight, int in_features, int out_features,
+                         uint8_t *idx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQLLM_B200_H */

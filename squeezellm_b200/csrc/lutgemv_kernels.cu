@@ -1,0 +1,952 @@
+// lutgemv_kernels.cu - B200 (sm_100a) dense-and-sparse LUT GEMV, written from scratch.
+//
+// Replaces (behaviour, not code) squeezellm/quant_cuda_kernel.cu of SqueezeAILab/SqueezeLLM:
+//   VecQuant{3,4}MatMulKernelNUQPerChannel[Batched]  (:741-1038)   LUT GEMV
+//   SPMV_ATOMIC[_BATCHED]                            (:1040-1089)  CSR outliers
+//   DenseMatVecKernel[Batched]                       (:1092-1164)  topX dense rows
+// and the 12 host launchers (:132-738), behind the C ABI of include/sqllm_b200.h.
+//
+// Design (DESIGN.md has the full story and the measurements):
+//   * ONE persistent launch per GEMV.  The [units x strips] iteration space (unit = one packed
+//     row for 4-bit, one 3-row / 32-input group for 3-bit; strip = 64 output columns) is flattened
+//     strip-major and cut into equal contiguous chunks, one per CTA (stream-K), so all SMs get the
+//     same number of bytes whatever the shape.  A CTA touches at most MAXSEG strips.
+//   * Each CTA stages, once: x (fp32) and the LUTs of its <= MAXSEG strips, transposed to
+//     [value][column-slot] so that every lane owns one shared-memory bank -> conflict-free gathers.
+//   * 8 "dense" warps stream the packed words with 128-bit read-only loads, register-prefetched
+//     PREFETCH deep, and turn every 4-bit index into an LDS address with a single PRMT (the table
+//     is 4 KB aligned, so address = {table_hi16, nibble|table_bits12-15, slot*4}); products are
+//     accumulated with packed fma.rn.f32x2.  No tensor cores: this is a gather-bound GEMV.
+//   * 1 "sparse" warp per CTA runs concurrently: it stages the CSR rows of the strips this CTA
+//     owns with cp.async and reduces them deterministically, and takes a slice of the topX dense
+//     rows.  Everything lands in the same fp32 accumulator before a single flush.
+//   * Flush: accumulate mode (the reference's 12 symbols; `mul` pre-filled by the caller) uses one
+//     red.add.f32 per (CTA, column).  Fused mode (QuantLinearLUT.forward fast path) writes partials to
+//     a workspace and the last-arriving CTA of each strip (atomic ticket, no spinning) sums them in
+//     fixed order, adds bias, converts and stores -> deterministic, no pre-zeroed output.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "sqllm_b200.h"
+
+namespace {
+
+constexpr int NW = 8;                 // dense warps per CTA
+constexpr int THREADS = (NW + 1) * 32;  // + 1 sparse warp
+constexpr int MAXSEG = 4;             // strips a CTA may touch
+constexpr int STRIP = 64;             // output columns per strip (16 lanes x 4 columns)
+constexpr int CSR_CH = 2048;          // CSR elements staged per chunk
+constexpr int PF4 = 4;                // 128-bit loads in flight per lane, 4-bit path
+constexpr int PF3 = 2;                // 3-row groups in flight per lane, 3-bit path
+constexpr int SROWS_LD = 68;          // padded row-pointer slice per segment (65 used)
+constexpr int MAX_TOPX_FUSED = 128;
+
+struct Params {
+    const uint32_t *qw;
+    const float *lut;
+    const void *x;      // fp32 or fp16 [K]
+    void *out;          // accumulate mode: float* mul ; fused: fp32/fp16 y
+    const float *bias;  // fused only, may be null
+    const int *rows, *cols;
+    const float *vals;
+    const float *full_rows;
+    const int *fri;
+    int topX;
+    int K, N;
+    int R;       // units per strip
+    int strips;
+    int T;       // strips * R
+    int chunk;   // units per CTA (even)
+    int hc;      // CTAs that take a slice of the dense rows
+    int hrows;   // k-rows per such CTA
+    int x_is_half, y_is_half;
+    int maxc;    // max dense contributors per strip (fused)
+    float *ws_part;   // [strips][maxc+1][64]
+    int *ws_cnt;      // [strips]
+    float *ws_hyb;    // [hc][topX]
+    int *ws_hyb_cnt;  // [1]
+    int has_csr_stage;
+};
+
+// ---- shared memory carve-up (offsets from a 4 KB aligned base) -----------------------------------
+template <int BITS>
+struct Smem {
+    static constexpr int TAB = (1 << BITS) * STRIP * 4;  // 4096 (w4) / 2048 (w3) bytes per segment
+    static constexpr int off_tab = 0;
+    static constexpr int off_part = off_tab + MAXSEG * TAB;                // float [MAXSEG][NW][64]
+    static constexpr int off_csr = off_part + MAXSEG * NW * STRIP * 4;     // float [MAXSEG][64]
+    static constexpr int off_srows = off_csr + MAXSEG * STRIP * 4;         // int   [MAXSEG][SROWS_LD]
+    static constexpr int off_misc = off_srows + MAXSEG * SROWS_LD * 4;     // int   [16] + float[MAX_TOPX_FUSED]
+    static constexpr int off_x = off_misc + 64 + MAX_TOPX_FUSED * 4;       // float [K]
+    __host__ __device__ static int off_stage(int K) { return off_x + K * 4; }  // int[CSR_CH] + float[CSR_CH]
+    __host__ __device__ static int total(int K, bool stage) { return 4096 + off_stage(K) + (stage ? CSR_CH * 8 : 0); }
+};
+
+// ---- small PTX helpers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_stream(const void *p) {  // read-once weights: bypass L1 allocation
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void ffma2(uint64_t &acc, uint64_t a, uint64_t b) {  // Blackwell packed fp32 FMA
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float sum2(uint64_t v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+__device__ __forceinline__ float warp_sum(float v) {  // fixed xor tree -> deterministic
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ float ldcg_f32(const float *p) { return __ldcg(p); }
+
+// Iterator over the units a dense warp processes: pairs of units (one per half-warp), round-robin.
+struct UnitIt {
+    int o;    // offset of the pair from the CTA's first unit
+    int rr;   // unit index inside the strip (even)
+    int seg;  // local segment
+    __device__ __forceinline__ void init(int warp, int r0, int R) {
+        o = 2 * warp;
+        rr = r0 + o;
+        seg = 0;
+        while (rr >= R) { rr -= R; ++seg; }
+    }
+    __device__ __forceinline__ void next(int R) {
+        o += 2 * NW;
+        rr += 2 * NW;
+        while (rr >= R) { rr -= R; ++seg; }
+    }
+};
+
+// =================================================================================================
+// 4-bit: one 128-bit word-quad (4 columns x 8 inputs) -> 32 gathers + 16 packed FMAs.
+//   E/O hold the even/odd nibbles of a word in separate bytes, already OR-ed with bits 12..15 of the
+//   table address; PRMT then builds the complete LDS address: {ls.b3, ls.b2, E.b_n, ls.b0}.
+// =================================================================================================
+__device__ __forceinline__ void consume4(const uint4 q, const int jsel, const uint32_t (&ls)[4], const uint32_t segc,
+                                         const uint32_t xaddr, uint64_t (&acc)[4]) {
+    const float4 xa = lds_v4(xaddr), xb = lds_v4(xaddr + 16);
+    const uint64_t x01 = pack2(xa.x, xa.y), x23 = pack2(xa.z, xa.w), x45 = pack2(xb.x, xb.y), x67 = pack2(xb.z, xb.w);
+    // half-warp 1 walks its 4 columns in the order 1,0,3,2 so that the two half-warps never hit the same bank
+    const uint32_t w[4] = {jsel ? q.y : q.x, jsel ? q.x : q.y, jsel ? q.w : q.z, jsel ? q.z : q.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const uint32_t E = (w[t] & 0x0F0F0F0Fu) | segc;
+        const uint32_t O = ((w[t] >> 4) & 0x0F0F0F0Fu) | segc;
+        const float e0 = lds_f32(__byte_perm(E, ls[t], 0x7604)), o0 = lds_f32(__byte_perm(O, ls[t], 0x7604));
+        const float e1 = lds_f32(__byte_perm(E, ls[t], 0x7614)), o1 = lds_f32(__byte_perm(O, ls[t], 0x7614));
+        const float e2 = lds_f32(__byte_perm(E, ls[t], 0x7624)), o2 = lds_f32(__byte_perm(O, ls[t], 0x7624));
+        const float e3 = lds_f32(__byte_perm(E, ls[t], 0x7634)), o3 = lds_f32(__byte_perm(O, ls[t], 0x7634));
+        ffma2(acc[t], pack2(e0, o0), x01);
+        ffma2(acc[t], pack2(e1, o1), x23);
+        ffma2(acc[t], pack2(e2, o2), x45);
+        ffma2(acc[t], pack2(e3, o3), x67);
+    }
+}
+
+// =================================================================================================
+// 3-bit: one group = 3 words per column = 32 inputs (10 | straddler | 10 | straddler | 10), the layout
+// of squeezellm/quant.py:185-203.  Each index is moved to bits 8..10 (table row stride 256 B) by one
+// shift (a funnel shift for the two straddlers) and merged with the lane's slot address by one LOP3.
+// =================================================================================================
+template <int SH>  // field at bit position SH of w -> bits 8..10
+__device__ __forceinline__ uint32_t fld(uint32_t w) {
+    if constexpr (SH < 8) return w << (8 - SH);
+    else if constexpr (SH == 8) return w;
+    else return w >> (SH - 8);
+}
+#define LK3(dst, word_expr, lsv) dst = lds_f32((((word_expr)) & 0x700u) | (lsv))
+
+__device__ __forceinline__ void consume3_col(const uint32_t w0, const uint32_t w1, const uint32_t w2, const uint32_t lsv,
+                                             const uint64_t (&xp)[16], uint64_t &acc) {
+    float a, b;
+    // inputs 0..9 from w0 (bits 3k), 10 straddles w0/w1
+    LK3(a, fld<0>(w0), lsv);  LK3(b, fld<3>(w0), lsv);  ffma2(acc, pack2(a, b), xp[0]);
+    LK3(a, fld<6>(w0), lsv);  LK3(b, fld<9>(w0), lsv);  ffma2(acc, pack2(a, b), xp[1]);
+    LK3(a, fld<12>(w0), lsv); LK3(b, fld<15>(w0), lsv); ffma2(acc, pack2(a, b), xp[2]);
+    LK3(a, fld<18>(w0), lsv); LK3(b, fld<21>(w0), lsv); ffma2(acc, pack2(a, b), xp[3]);
+    LK3(a, fld<24>(w0), lsv); LK3(b, fld<27>(w0), lsv); ffma2(acc, pack2(a, b), xp[4]);
+    LK3(a, __funnelshift_r(w0, w1, 22), lsv);            // input 10: bits 30,31 of w0 + bit 0 of w1
+    LK3(b, fld<1>(w1), lsv);                             // input 11
+    ffma2(acc, pack2(a, b), xp[5]);
+    LK3(a, fld<4>(w1), lsv);  LK3(b, fld<7>(w1), lsv);  ffma2(acc, pack2(a, b), xp[6]);
+    LK3(a, fld<10>(w1), lsv); LK3(b, fld<13>(w1), lsv); ffma2(acc, pack2(a, b), xp[7]);
+    LK3(a, fld<16>(w1), lsv); LK3(b, fld<19>(w1), lsv); ffma2(acc, pack2(a, b), xp[8]);
+    LK3(a, fld<22>(w1), lsv); LK3(b, fld<25>(w1), lsv); ffma2(acc, pack2(a, b), xp[9]);
+    LK3(a, fld<28>(w1), lsv);                            // input 20
+    LK3(b, __funnelshift_r(w1, w2, 23), lsv);            // input 21: bit 31 of w1 + bits 0,1 of w2
+    ffma2(acc, pack2(a, b), xp[10]);
+    LK3(a, fld<2>(w2), lsv);  LK3(b, fld<5>(w2), lsv);  ffma2(acc, pack2(a, b), xp[11]);
+    LK3(a, fld<8>(w2), lsv);  LK3(b, fld<11>(w2), lsv); ffma2(acc, pack2(a, b), xp[12]);
+    LK3(a, fld<14>(w2), lsv); LK3(b, fld<17>(w2), lsv); ffma2(acc, pack2(a, b), xp[13]);
+    LK3(a, fld<20>(w2), lsv); LK3(b, fld<23>(w2), lsv); ffma2(acc, pack2(a, b), xp[14]);
+    LK3(a, fld<26>(w2), lsv); LK3(b, fld<29>(w2), lsv); ffma2(acc, pack2(a, b), xp[15]);
+}
+
+struct Grp3 { uint4 a, b, c; };
+
+__device__ __forceinline__ void consume3(const Grp3 &g, const int jsel, const uint32_t (&ls)[4], const uint32_t xaddr,
+                                         uint64_t (&acc)[4]) {
+    uint64_t xp[16];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const float4 f = lds_v4(xaddr + 16 * v);
+        xp[2 * v] = pack2(f.x, f.y);
+        xp[2 * v + 1] = pack2(f.z, f.w);
+    }
+    const uint32_t a[4] = {jsel ? g.a.y : g.a.x, jsel ? g.a.x : g.a.y, jsel ? g.a.w : g.a.z, jsel ? g.a.z : g.a.w};
+    const uint32_t b[4] = {jsel ? g.b.y : g.b.x, jsel ? g.b.x : g.b.y, jsel ? g.b.w : g.b.z, jsel ? g.b.z : g.b.w};
+    const uint32_t c[4] = {jsel ? g.c.y : g.c.x, jsel ? g.c.x : g.c.y, jsel ? g.c.w : g.c.z, jsel ? g.c.z : g.c.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) consume3_col(a[t], b[t], c[t], ls[t], xp, acc[t]);
+}
+
+// ---- per-column final reduction of a strip's workspace partials (fused mode) ----------------------
+__device__ __forceinline__ void final_store(const Params &p, int strip, int c, int nd, bool hyb) {
+    const int col = strip * STRIP + c;
+    if (col >= p.N) return;
+    const float *base = p.ws_part + (size_t)strip * (p.maxc + 1) * STRIP + c;
+    float tot = 0.f;
+    for (int s = 0; s < nd; ++s) tot += ldcg_f32(base + s * STRIP);
+    if (hyb) tot += ldcg_f32(base + p.maxc * STRIP);
+    if (p.bias) tot += p.bias[col];
+    if (p.y_is_half) reinterpret_cast<__half *>(p.out)[col] = __float2half_rn(tot);
+    else reinterpret_cast<float *>(p.out)[col] = tot;
+}
+
+__device__ __forceinline__ bool strip_has_hybrid(const Params &p, int strip) {
+    if (!p.full_rows) return false;
+    bool h = false;
+    for (int j = 0; j < p.topX; ++j) {
+        const int c = __ldg(p.fri + j);
+        h |= (c >= 0 && c < p.N && c / STRIP == strip);
+    }
+    return h;
+}
+
+// =================================================================================================
+// The kernel
+// =================================================================================================
+template <int BITS, bool FUSED>
+__global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
+    using S = Smem<BITS>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 4095) & ~uintptr_t(4095));
+    const uint32_t sm_u32 = smem_u32(sm);
+    float *part = reinterpret_cast<float *>(sm + S::off_part);
+    float *csr_acc = reinterpret_cast<float *>(sm + S::off_csr);
+    int *srows = reinterpret_cast<int *>(sm + S::off_srows);
+    int *misc = reinterpret_cast<int *>(sm + S::off_misc);
+    float *hyb_tot = reinterpret_cast<float *>(sm + S::off_misc + 64);
+    float *xs = reinterpret_cast<float *>(sm + S::off_x);
+    const uint32_t xs_u32 = sm_u32 + S::off_x;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = p.K, N = p.N, R = p.R;
+
+    // ---- this CTA's chunk of the flattened [strip][unit] space ----
+    const int g0 = min((int)blockIdx.x * p.chunk, p.T);
+    const int g1 = min(g0 + p.chunk, p.T);
+    const int len = g1 - g0;
+    const int s0 = g0 / R;
+    const int r0 = g0 - s0 * R;
+    const int nseg = len > 0 ? (g1 - 1) / R - s0 + 1 : 0;
+
+    // ---- stage LUTs (transposed to [value][slot]) and x ----
+    {
+        constexpr int L = 1 << BITS;
+        const int nel = nseg * STRIP * L;
+        for (int e = tid; e < nel; e += THREADS) {
+            const int v = e & (L - 1);
+            const int c = (e >> BITS) & (STRIP - 1);
+            const int seg = e >> (BITS + 6);
+            const int col = (s0 + seg) * STRIP + c;
+            const int slot = ((c & 3) << 4) | (c >> 2);
+            const uint32_t dst = sm_u32 + S::off_tab + seg * S::TAB + v * (STRIP * 4) + slot * 4;
+            if (col < N) cp_async4(dst, p.lut + (size_t)col * L + v);
+            else *reinterpret_cast<float *>(sm + S::off_tab + seg * S::TAB + v * (STRIP * 4) + slot * 4) = 0.f;
+        }
+        if (p.x_is_half) {
+            const uint4 *xh = reinterpret_cast<const uint4 *>(p.x);
+            for (int e = tid; e < K / 8; e += THREADS) {
+                const uint4 u = __ldg(xh + e);
+                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+                const float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+                reinterpret_cast<float4 *>(xs)[2 * e] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                reinterpret_cast<float4 *>(xs)[2 * e + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+            }
+        } else {
+            const float *xf = reinterpret_cast<const float *>(p.x);
+            for (int e = tid; e < K / 4; e += THREADS) cp_async16(xs_u32 + 16 * e, xf + 4 * e);
+        }
+        cp_async_commit();
+        for (int e = tid; e < MAXSEG * NW * STRIP; e += THREADS) part[e] = 0.f;
+        for (int e = tid; e < MAXSEG * STRIP; e += THREADS) csr_acc[e] = 0.f;
+    }
+
+    const int i16 = lane & 15, jsel = lane >> 4;
+
+    if (warp < NW) {
+        // =========================== dense warps ===========================
+        uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+        uint32_t ls[4] = {0u, 0u, 0u, 0u};
+        uint32_t segc = 0u;
+        int cur_seg = -1;
+
+        auto set_seg = [&](int seg) {
+            const uint32_t tb = sm_u32 + S::off_tab + seg * S::TAB;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t slot4 = ((((t ^ jsel) << 4) | i16) << 2);
+                if (BITS == 4) ls[t] = (tb & 0xFFFF0000u) | slot4;  // byte1 comes from the nibble | segc
+                else ls[t] = tb + slot4;                            // 2 KB aligned: bits 8..10 are free
+            }
+            segc = ((tb >> 8) & 0xF0u) * 0x01010101u;
+        };
+        auto deposit = [&](int seg) {
+            float s[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) s[t] = sum2(acc[t]);
+            // lane (i, j=1) holds column t^1 in slot t: hand it to lane (i, j=0)
+            const float v0 = __shfl_xor_sync(0xffffffffu, s[1], 16);
+            const float v1 = __shfl_xor_sync(0xffffffffu, s[0], 16);
+            const float v2 = __shfl_xor_sync(0xffffffffu, s[3], 16);
+            const float v3 = __shfl_xor_sync(0xffffffffu, s[2], 16);
+            if (jsel == 0)
+                *reinterpret_cast<float4 *>(part + (seg * NW + warp) * STRIP + 4 * i16) =
+                    make_float4(s[0] + v0, s[1] + v1, s[2] + v2, s[3] + v3);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[t] = 0ull;
+        };
+
+        UnitIt ld, cs;
+        ld.init(warp, r0, R);
+        cs.init(warp, r0, R);
+
+        if (BITS == 4) {
+            uint4 buf[PF4];
+            auto load4 = [&](const UnitIt &it) -> uint4 {
+                const int col0 = (s0 + it.seg) * STRIP + 4 * i16;
+                if (it.o < len && col0 < N) return ldg_stream(p.qw + (size_t)(it.rr + jsel) * N + col0);
+                return make_uint4(0u, 0u, 0u, 0u);
+            };
+#pragma unroll
+            for (int u = 0; u < PF4; ++u) { buf[u] = load4(ld); ld.next(R); }
+            cp_async_wait_all();
+            __syncthreads();  // LUTs, x, zeroed partials visible
+            while (cs.o < len) {
+#pragma unroll
+                for (int u = 0; u < PF4; ++u) {
+                    if (cs.o < len) {
+                        if (cs.seg != cur_seg) {
+                            if (cur_seg >= 0) deposit(cur_seg);
+                            cur_seg = cs.seg;
+                            set_seg(cur_seg);
+                        }
+                        consume4(buf[u], jsel, ls, segc, xs_u32 + 32 * (cs.rr + jsel), acc);
+                        buf[u] = load4(ld);
+                        ld.next(R);
+                        cs.next(R);
+                    }
+                }
+            }
+        } else {
+            Grp3 buf[PF3];
+            auto load3 = [&](const UnitIt &it) -> Grp3 {
+                Grp3 g;
+                const int col0 = (s0 + it.seg) * STRIP + 4 * i16;
+                if (it.o < len && col0 < N) {
+                    const uint32_t *q = p.qw + (size_t)(3 * (it.rr + jsel)) * N + col0;
+                    g.a = ldg_stream(q);
+                    g.b = ldg_stream(q + N);
+                    g.c = ldg_stream(q + 2 * (size_t)N);
+                } else {
+                    g.a = g.b = g.c = make_uint4(0u, 0u, 0u, 0u);
+                }
+                return g;
+            };
+#pragma unroll
+            for (int u = 0; u < PF3; ++u) { buf[u] = load3(ld); ld.next(R); }
+            cp_async_wait_all();
+            __syncthreads();
+            while (cs.o < len) {
+#pragma unroll
+                for (int u = 0; u < PF3; ++u) {
+                    if (cs.o < len) {
+                        if (cs.seg != cur_seg) {
+                            if (cur_seg >= 0) deposit(cur_seg);
+                            cur_seg = cs.seg;
+                            set_seg(cur_seg);
+                        }
+                        consume3(buf[u], jsel, ls, xs_u32 + 128 * (cs.rr + jsel), acc);
+                        buf[u] = load3(ld);
+                        ld.next(R);
+                        cs.next(R);
+                    }
+                }
+            }
+        }
+        if (cur_seg >= 0) deposit(cur_seg);
+    } else {
+        // =========================== sparse warp ===========================
+        // (1) row pointers of the strips whose first unit lives in this CTA
+        if (p.rows) {
+            for (int seg = 0; seg < nseg; ++seg) {
+                const bool owner = (seg > 0) || (r0 == 0);
+                if (!owner) continue;
+                const int c0 = (s0 + seg) * STRIP;
+                const int nc = min(STRIP, N - c0);
+                for (int t = lane; t <= nc; t += 32) srows[seg * SROWS_LD + t] = __ldg(p.rows + c0 + t);
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();  // matches the dense warps' barrier: x is in shared memory now
+
+        // (2) CSR outliers: deterministic per-row sums into csr_acc
+        if (p.rows) {
+            int *scols = reinterpret_cast<int *>(sm + S::off_stage(K));
+            float *svals = reinterpret_cast<float *>(sm + S::off_stage(K) + CSR_CH * 4);
+            const uint32_t scols_u32 = sm_u32 + S::off_stage(K), svals_u32 = scols_u32 + CSR_CH * 4;
+            for (int seg = 0; seg < nseg; ++seg) {
+                const bool owner = (seg > 0) || (r0 == 0);
+                if (!owner) continue;
+                const int c0 = (s0 + seg) * STRIP;
+                const int nc = min(STRIP, N - c0);
+                const int *sr = srows + seg * SROWS_LD;
+                float *out = csr_acc + seg * STRIP;
+                int cb = 0;
+                while (cb < nc) {
+                    const int base = sr[cb];
+                    int ce = cb + 1;
+                    while (ce < nc && sr[ce + 1] - base <= CSR_CH) ++ce;
+                    const int cnt = sr[ce] - base;
+                    if (cnt > CSR_CH) {  // one very long row: straight from global memory
+                        float a = 0.f;
+                        for (int e = base + lane; e < sr[cb + 1]; e += 32) a += __ldg(p.vals + e) * xs[__ldg(p.cols + e)];
+                        a = warp_sum(a);
+                        if (lane == 0) out[cb] = a;
+                        cb += 1;
+                        continue;
+                    }
+                    for (int e = lane; e < cnt; e += 32) {
+                        cp_async4(scols_u32 + 4 * e, p.cols + base + e);
+                        cp_async4(svals_u32 + 4 * e, p.vals + base + e);
+                    }
+                    cp_async_commit();
+                    cp_async_wait_all();
+                    __syncwarp();
+                    // pass 1: one lane per short row (sequential sum in storage order)
+                    for (int c = cb + lane; c < ce; c += 32) {
+                        const int a0 = sr[c] - base, a1 = sr[c + 1] - base;
+                        if (a1 - a0 <= 64) {
+                            float a = 0.f;
+                            for (int e = a0; e < a1; ++e) a += svals[e] * xs[scols[e]];
+                            out[c] = a;
+                        }
+                    }
+                    // pass 2: the whole warp on each long row
+                    for (int c = cb; c < ce; ++c) {
+                        const int a0 = sr[c] - base, a1 = sr[c + 1] - base;
+                        if (a1 - a0 > 64) {
+                            float a = 0.f;
+                            for (int e = a0 + lane; e < a1; e += 32) a += svals[e] * xs[scols[e]];
+                            a = warp_sum(a);
+                            if (lane == 0) out[c] = a;
+                        }
+                    }
+                    __syncwarp();
+                    cb = ce;
+                }
+            }
+        }
+
+        // (3) topX dense rows: CTA b < hc takes k-rows [b*hrows, (b+1)*hrows)
+        if (p.full_rows && (int)blockIdx.x < p.hc) {
+            const int kb = blockIdx.x * p.hrows, ke = min(K, kb + p.hrows);
+            for (int jb = 0; jb < p.topX; jb += 32) {
+                const int j = jb + lane;
+                float a = 0.f;
+                if (j < p.topX) {
+                    const float *fr = p.full_rows + (size_t)kb * p.topX + j;
+#pragma unroll 8
+                    for (int k = kb; k < ke; ++k, fr += p.topX) a += __ldg(fr) * xs[k];
+                    if (FUSED) {
+                        p.ws_hyb[(size_t)blockIdx.x * p.topX + j] = a;
+                    } else {
+                        const int c = __ldg(p.fri + j);
+                        if (c >= 0 && c < N) atomicAdd(reinterpret_cast<float *>(p.out) + c, a);
+                    }
+                }
+            }
+            if (FUSED) {
+                __syncwarp();
+                int last = 0;
+                if (lane == 0) {
+                    __threadfence();
+                    last = (atomicAdd(p.ws_hyb_cnt, 1) == p.hc - 1);
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    __threadfence();
+                    if (lane == 0) *p.ws_hyb_cnt = 0;
+                    for (int j = lane; j < p.topX; j += 32) {
+                        float t = 0.f;
+                        for (int b = 0; b < p.hc; ++b) t += ldcg_f32(p.ws_hyb + (size_t)b * p.topX + j);
+                        hyb_tot[j] = t;
+                    }
+                    __syncwarp();
+                    // hand one "hybrid slot" vector to every strip that owns a dense-row output channel
+                    for (int j0 = 0; j0 < p.topX; ++j0) {
+                        const int cj0 = __ldg(p.fri + j0);
+                        if (cj0 < 0 || cj0 >= N) continue;
+                        const int strip = cj0 / STRIP;
+                        bool seen = false;
+                        for (int j = 0; j < j0; ++j) {
+                            const int cj = __ldg(p.fri + j);
+                            seen |= (cj >= 0 && cj < N && cj / STRIP == strip);
+                        }
+                        if (seen) continue;
+                        float v0 = 0.f, v1 = 0.f;  // columns lane, lane+32 of the strip
+                        for (int j = j0; j < p.topX; ++j) {
+                            const int cj = __ldg(p.fri + j);
+                            if (cj >= 0 && cj < N && cj / STRIP == strip) {
+                                const int cc = cj - strip * STRIP;
+                                if (cc == lane) v0 += hyb_tot[j];
+                                if (cc == lane + 32) v1 += hyb_tot[j];
+                            }
+                        }
+                        float *slot = p.ws_part + ((size_t)strip * (p.maxc + 1) + p.maxc) * STRIP;
+                        slot[lane] = v0;
+                        slot[lane + 32] = v1;
+                        __syncwarp();
+                        const int first = (int)(((long long)strip * R) / p.chunk);
+                        const int lastc = (int)((((long long)strip + 1) * R - 1) / p.chunk);
+                        const int nd = lastc - first + 1;
+                        int fin = 0;
+                        if (lane == 0) {
+                            __threadfence();
+                            fin = (atomicAdd(p.ws_cnt + strip, 1) == nd);  // nd dense contributors + this one
+                            if (fin) p.ws_cnt[strip] = 0;
+                        }
+                        fin = __shfl_sync(0xffffffffu, fin, 0);
+                        if (fin) {
+                            __threadfence();
+                            final_store(p, strip, lane, nd, true);
+                            final_store(p, strip, lane + 32, nd, true);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    __syncthreads();  // all partials of this CTA are in shared memory
+
+    // =========================== flush ===========================
+    if (tid < MAXSEG * STRIP) {
+        const int seg = tid >> 6, c = tid & 63;
+        const bool active = seg < nseg;
+        float tot = 0.f;
+        int strip = 0, nd = 1, slot = 0;
+        bool hyb = false;
+        if (active) {
+            strip = s0 + seg;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) tot += part[(seg * NW + w) * STRIP + c];
+            tot += csr_acc[seg * STRIP + c];
+        }
+        if (!FUSED) {
+            const int col = strip * STRIP + c;
+            if (active && col < N) atomicAdd(reinterpret_cast<float *>(p.out) + col, tot);
+            return;
+        }
+        if (active) {
+            const int first = (int)(((long long)strip * R) / p.chunk);
+            const int lastc = (int)((((long long)strip + 1) * R - 1) / p.chunk);
+            nd = lastc - first + 1;
+            slot = (int)blockIdx.x - first;
+            hyb = strip_has_hybrid(p, strip);
+            if (nd == 1 && !hyb) {  // this CTA owns the whole strip: store directly
+                const int col = strip * STRIP + c;
+                if (col < N) {
+                    if (p.bias) tot += p.bias[col];
+                    if (p.y_is_half) reinterpret_cast<__half *>(p.out)[col] = __float2half_rn(tot);
+                    else reinterpret_cast<float *>(p.out)[col] = tot;
+                }
+            } else {
+                p.ws_part[((size_t)strip * (p.maxc + 1) + slot) * STRIP + c] = tot;
+            }
+        }
+        // ticket: 64 threads (2 warps) per segment; sync them with a named barrier per segment
+        const bool ticketed = active && !(nd == 1 && !hyb);
+        asm volatile("bar.sync %0, 64;" ::"r"(seg + 1));
+        if (c == 0) {
+            int fin = 0;
+            if (ticketed) {
+                __threadfence();
+                fin = (atomicAdd(p.ws_cnt + strip, 1) == nd + (hyb ? 1 : 0) - 1);
+                if (fin) p.ws_cnt[strip] = 0;
+            }
+            misc[seg] = fin;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(seg + 1));
+        if (misc[seg]) {
+            __threadfence();
+            final_store(p, strip, c, nd, hyb);
+        }
+    }
+}
+
+// test hook: unpack exactly like the GEMV path (same shift/mask expressions)
+__global__ void unpack_kernel(int bits, const uint32_t *__restrict__ q, int K, int N, uint8_t *__restrict__ idx) {
+    const size_t n = (size_t)K * N;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e / N), c = (int)(e % N);
+        uint32_t v;
+        if (bits == 4) {
+            const uint32_t w = q[(size_t)(k >> 3) * N + c];
+            const int n8 = k & 7;
+            const uint32_t EO = (n8 & 1) ? ((w >> 4) & 0x0F0F0F0Fu) : (w & 0x0F0F0F0Fu);
+            v = __byte_perm(EO, 0u, 0x4440 | (n8 >> 1)) & 0xFFu;
+        } else {
+            const int g = k >> 5, j = k & 31;
+            const uint32_t *pq = q + (size_t)(3 * g) * N + c;
+            const uint32_t w0 = pq[0], w1 = pq[N], w2 = pq[2 * (size_t)N];
+            uint32_t f;  // field moved to bits 8..10, as in consume3_col
+            if (j < 10) f = (3 * j < 8) ? (w0 << (8 - 3 * j)) : (w0 >> (3 * j - 8));
+            else if (j == 10) f = __funnelshift_r(w0, w1, 22);
+            else if (j < 21) { const int s = 1 + 3 * (j - 11); f = (s < 8) ? (w1 << (8 - s)) : (w1 >> (s - 8)); }
+            else if (j == 21) f = __funnelshift_r(w1, w2, 23);
+            else { const int s = 2 + 3 * (j - 22); f = (s < 8) ? (w2 << (8 - s)) : (w2 >> (s - 8)); }
+            v = (f & 0x700u) >> 8;
+        }
+        idx[e] = (uint8_t)v;
+    }
+}
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+struct DevInfo { int sm = 0; int occ[2][2] = {{0, 0}, {0, 0}}; int occ_smem[2][2] = {{-1, -1}, {-1, -1}}; bool attr_set = false; };
+DevInfo g_dev[64];
+
+template <int BITS, bool FUSED>
+int occupancy(int smem) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lutgemv_kernel<BITS, FUSED>, THREADS, smem);
+    return occ;
+}
+
+struct Plan {
+    int R, strips, T, chunk, G, maxc, hc, hrows, smem;
+    size_t ws_cnt_off, ws_hybcnt_off, ws_hyb_off, ws_part_off, ws_bytes;
+};
+
+int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &pl) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(SQLLM_ECUDA, "cudaGetDevice failed");
+    if (dev < 0 || dev >= 64) return fail(SQLLM_EINVAL, "device ordinal %d out of range", dev);
+    DevInfo &d = g_dev[dev];
+    if (d.sm == 0) {
+        if (cudaDeviceGetAttribute(&d.sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.sm <= 0)
+            return fail(SQLLM_ECUDA, "cannot query SM count");
+    }
+    if (!d.attr_set) {
+        const int mx = 227 * 1024;
+        cudaFuncSetAttribute(lutgemv_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(lutgemv_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(lutgemv_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(lutgemv_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (cudaGetLastError() != cudaSuccess) return fail(SQLLM_ECUDA, "cudaFuncSetAttribute failed");
+        d.attr_set = true;
+    }
+    pl.smem = bits == 4 ? Smem<4>::total(K, has_csr) : Smem<3>::total(K, has_csr);
+    if (pl.smem > 227 * 1024) return fail(SQLLM_EINVAL, "in_features=%d needs %d B of shared memory (> 227 KB)", K, pl.smem);
+    const int bi = bits == 4 ? 1 : 0, fi = fused ? 1 : 0;
+    if (d.occ_smem[bi][fi] != pl.smem) {
+        int o = bits == 4 ? (fused ? occupancy<4, true>(pl.smem) : occupancy<4, false>(pl.smem))
+                          : (fused ? occupancy<3, true>(pl.smem) : occupancy<3, false>(pl.smem));
+        if (o <= 0) return fail(SQLLM_ECUDA, "kernel cannot be resident (smem %d B)", pl.smem);
+        d.occ[bi][fi] = o;
+        d.occ_smem[bi][fi] = pl.smem;
+    }
+    pl.R = bits == 4 ? K / 8 : K / 32;
+    pl.strips = (N + STRIP - 1) / STRIP;
+    const long long T = (long long)pl.strips * pl.R;
+    if (T > 0x3fffffff) return fail(SQLLM_EINVAL, "problem too large");
+    pl.T = (int)T;
+    int G = d.sm * d.occ[bi][fi];
+    int chunk = (int)(2 * ((T + 2LL * G - 1) / (2LL * G)));
+    if (chunk > 3 * pl.R) chunk = 3 * pl.R;  // a CTA may touch at most MAXSEG strips
+    if (chunk < 2) chunk = 2;
+    pl.chunk = chunk;
+    pl.G = (int)((T + chunk - 1) / chunk);
+    pl.maxc = (pl.R - 1) / chunk + 2;
+    pl.hc = 0;
+    pl.hrows = 0;
+    if (topX > 0) {
+        int hc = pl.G < K / 16 ? pl.G : K / 16;
+        if (hc < 1) hc = 1;
+        pl.hrows = (K + hc - 1) / hc;
+        pl.hc = (K + pl.hrows - 1) / pl.hrows;
+    }
+    size_t off = 0;
+    pl.ws_cnt_off = off; off += (size_t)pl.strips * 4;
+    pl.ws_hybcnt_off = off; off += 4;
+    off = (off + 255) & ~(size_t)255;
+    pl.ws_hyb_off = off; off += (size_t)pl.hc * (topX > 0 ? topX : 0) * 4;
+    off = (off + 255) & ~(size_t)255;
+    pl.ws_part_off = off; off += (size_t)pl.strips * (pl.maxc + 1) * STRIP * 4;
+    pl.ws_bytes = off;
+    return SQLLM_OK;
+}
+
+int check_common(const sqllm_lutgemv_args *a) {
+    if (!a) return fail(SQLLM_EINVAL, "null args");
+    if (a->bits != 3 && a->bits != 4) return fail(SQLLM_EINVAL, "bits must be 3 or 4 (got %d)", a->bits);
+    if (a->in_features <= 0 || a->in_features % 64) return fail(SQLLM_EINVAL, "in_features=%d must be a positive multiple of 64", a->in_features);
+    if (a->out_features <= 0 || a->out_features % 4) return fail(SQLLM_EINVAL, "out_features=%d must be a positive multiple of 4", a->out_features);
+    if (!a->qweight || !a->lookup_table) return fail(SQLLM_EINVAL, "qweight / lookup_table must not be null");
+    if (reinterpret_cast<uintptr_t>(a->qweight) & 15) return fail(SQLLM_EINVAL, "qweight must be 16-byte aligned");
+    if (a->rows && (!a->cols || !a->vals)) return fail(SQLLM_EINVAL, "rows given without cols/vals");
+    if (a->topX < 0) return fail(SQLLM_EINVAL, "topX < 0");
+    if (a->full_rows && a->topX > 0 && !a->full_row_indices) return fail(SQLLM_EINVAL, "full_rows given without full_row_indices");
+    return SQLLM_OK;
+}
+
+template <bool FUSED>
+int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t st) {
+    p.qw = reinterpret_cast<const uint32_t *>(a->qweight);
+    p.lut = a->lookup_table;
+    p.rows = a->rows; p.cols = a->cols; p.vals = a->vals;
+    const bool hyb = a->full_rows && a->topX > 0;
+    p.full_rows = hyb ? a->full_rows : nullptr;
+    p.fri = hyb ? a->full_row_indices : nullptr;
+    p.topX = hyb ? a->topX : 0;
+    p.K = a->in_features; p.N = a->out_features;
+    p.R = pl.R; p.strips = pl.strips; p.T = pl.T; p.chunk = pl.chunk;
+    p.hc = hyb ? pl.hc : 0; p.hrows = pl.hrows; p.maxc = pl.maxc;
+    p.has_csr_stage = a->rows ? 1 : 0;
+    if (a->bits == 4) lutgemv_kernel<4, FUSED><<<pl.G, THREADS, pl.smem, st>>>(p);
+    else lutgemv_kernel<3, FUSED><<<pl.G, THREADS, pl.smem, st>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SQLLM_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return SQLLM_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int sqllm_abi_version(void) { return SQLLM_ABI_VERSION; }
+const char *sqllm_last_error(void) { return g_err; }
+
+int sqllm_device_sm_count(void) {
+    int dev = 0, sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return sm;
+}
+
+size_t sqllm_workspace_bytes(int bits, int in_features, int out_features, int topX) {
+    Plan pl;
+    if (bits != 3 && bits != 4) return 0;
+    if (in_features <= 0 || in_features % 64 || out_features <= 0) return 0;
+    // worst case over csr staging on/off: the larger shared-memory footprint gives the smaller grid,
+    // hence the larger chunk; take the max of both plans.
+    size_t b = 0;
+    for (int csr = 0; csr < 2; ++csr)
+        if (make_plan(bits, in_features, out_features, topX, csr != 0, true, pl) == SQLLM_OK && pl.ws_bytes > b) b = pl.ws_bytes;
+    return b;
+}
+
+int sqllm_lutgemv(const sqllm_lutgemv_args *a, void *stream) {
+    int rc = check_common(a);
+    if (rc) return rc;
+    if (!a->vec || !a->mul) return fail(SQLLM_EINVAL, "vec / mul must not be null");
+    if (a->batch < 1) return fail(SQLLM_EINVAL, "batch must be >= 1");
+    if (reinterpret_cast<uintptr_t>(a->vec) & 15) return fail(SQLLM_EINVAL, "vec must be 16-byte aligned");
+    const bool hyb = a->full_rows && a->topX > 0;
+    Plan pl;
+    rc = make_plan(a->bits, a->in_features, a->out_features, hyb ? a->topX : 0, a->rows != nullptr, false, pl);
+    if (rc) return rc;
+    Params p;
+    memset(&p, 0, sizeof(p));
+    for (int b = 0; b < a->batch; ++b) {  // serial over batch rows, like the reference's in-kernel `for b` (:1011)
+        p.x = a->vec + (size_t)b * a->in_features;
+        p.out = a->mul + (size_t)b * a->out_features;
+        p.x_is_half = 0;
+        rc = launch<false>(a, pl, p, static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+    }
+    return SQLLM_OK;
+}
+
+int sqllm_lutgemv_fused(const sqllm_lutgemv_args *a, const void *x, int x_is_half, void *y, int y_is_half,
+                        const float *bias, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = check_common(a);
+    if (rc) return rc;
+    if (!x || !y) return fail(SQLLM_EINVAL, "x / y must not be null");
+    if (reinterpret_cast<uintptr_t>(x) & 15) return fail(SQLLM_EINVAL, "x must be 16-byte aligned");
+    const bool hyb = a->full_rows && a->topX > 0;
+    if (hyb && a->topX > MAX_TOPX_FUSED) return fail(SQLLM_EINVAL, "fused path supports topX <= %d", MAX_TOPX_FUSED);
+    Plan pl;
+    rc = make_plan(a->bits, a->in_features, a->out_features, hyb ? a->topX : 0, a->rows != nullptr, true, pl);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < pl.ws_bytes)
+        return fail(SQLLM_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.ws_bytes, workspace_bytes);
+    Params p;
+    memset(&p, 0, sizeof(p));
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    p.ws_cnt = reinterpret_cast<int *>(ws + pl.ws_cnt_off);
+    p.ws_hyb_cnt = reinterpret_cast<int *>(ws + pl.ws_hybcnt_off);
+    p.ws_hyb = reinterpret_cast<float *>(ws + pl.ws_hyb_off);
+    p.ws_part = reinterpret_cast<float *>(ws + pl.ws_part_off);
+    p.x = x; p.x_is_half = x_is_half; p.out = y; p.y_is_half = y_is_half; p.bias = bias;
+    return launch<true>(a, pl, p, static_cast<cudaStream_t>(stream));
+}
+
+int sqllm_unpack_indices(int bits, const int32_t *qweight, int in_features, int out_features, uint8_t *idx, void *stream) {
+    if ((bits != 3 && bits != 4) || !qweight || !idx || in_features % 32 || in_features <= 0 || out_features <= 0)
+        return fail(SQLLM_EINVAL, "bad arguments to sqllm_unpack_indices");
+    unpack_kernel<<<1024, 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, reinterpret_cast<const uint32_t *>(qweight),
+                                                                       in_features, out_features, idx);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SQLLM_ECUDA, "unpack launch failed: %s", cudaGetErrorString(e));
+    return SQLLM_OK;
+}
+
+// ---- the reference's 12 launchers -----------------------------------------------------------------
+static int run12(int bits, const float *vec, const int32_t *mat, float *mul, const float *lut, int height, int width,
+                 int batch, int vec_height, const int32_t *rows, const int32_t *cols, const float *vals, int num_rows,
+                 const float *full_rows, const int32_t *fri, int fr_height, int fr_width, void *stream) {
+    sqllm_lutgemv_args a;
+    memset(&a, 0, sizeof(a));
+    a.bits = bits;
+    if (height <= 0 || height % bits) return fail(SQLLM_EINVAL, "height=%d is not a multiple of bits=%d", height, bits);
+    a.in_features = height / bits * 32;
+    a.out_features = width;
+    a.batch = batch;
+    if (vec_height >= 0 && vec_height != a.in_features)
+        return fail(SQLLM_EINVAL, "vec has %d features, packed matrix implies %d", vec_height, a.in_features);
+    if (rows && num_rows != width) return fail(SQLLM_EINVAL, "num_rows=%d must equal the matrix width %d", num_rows, width);
+    if (full_rows && fr_height != a.in_features)
+        return fail(SQLLM_EINVAL, "full_rows has %d rows, expected in_features=%d", fr_height, a.in_features);
+    a.qweight = mat; a.lookup_table = lut; a.vec = vec; a.mul = mul;
+    a.rows = rows; a.cols = cols; a.vals = vals;
+    a.full_rows = full_rows; a.full_row_indices = fri; a.topX = full_rows ? fr_width : 0;
+    return sqllm_lutgemv(&a, stream);
+}
+
+int sqllm_vecquant3matmul_nuq_perchannel(const float *vec, const int32_t *mat, float *mul, const float *lut, int height,
+                                         int width, void *stream) {
+    return run12(3, vec, mat, mul, lut, height, width, 1, -1, 0, 0, 0, 0, 0, 0, 0, 0, stream);
+}
+int sqllm_vecquant4matmul_nuq_perchannel(const float *vec, const int32_t *mat, float *mul, const float *lut, int height,
+                                         int width, void *stream) {
+    return run12(4, vec, mat, mul, lut, height, width, 1, -1, 0, 0, 0, 0, 0, 0, 0, 0, stream);
+}
+int sqllm_vecquant3matmul_nuq_perchannel_batched(const float *vec, const int32_t *mat, float *mul, const float *lut,
+                                                 int height, int width, int batch, int vec_height, void *stream) {
+    return run12(3, vec, mat, mul, lut, height, width, batch, vec_height, 0, 0, 0, 0, 0, 0, 0, 0, stream);
+}
+int sqllm_vecquant4matmul_nuq_perchannel_batched(const float *vec, const int32_t *mat, float *mul, const float *lut,
+                                                 int height, int width, int batch, int vec_height, void *stream) {
+    return run12(4, vec, mat, mul, lut, height, width, batch, vec_height, 0, 0, 0, 0, 0, 0, 0, 0, stream);
+}
+int sqllm_vecquant3matmul_spmv_nuq_perchannel(const int32_t *rows, const int32_t *cols, const float *mat, const float *vec,
+                                              float *mul, int num_rows, const int32_t *mat3, const float *lut, int height,
+                                              int width, void *stream) {
+    return run12(3, vec, mat3, mul, lut, height, width, 1, -1, rows, cols, mat, num_rows, 0, 0, 0, 0, stream);
+}
+int sqllm_vecquant4matmul_spmv_nuq_perchannel(const int32_t *rows, const int32_t *cols, const float *mat, const float *vec,
+                                              float *mul, int num_rows, const int32_t *mat4, const float *lut, int height,
+                                              int width, void *stream) {
+    return run12(4, vec, mat4, mul, lut, height, width, 1, -1, rows, cols, mat, num_rows, 0, 0, 0, 0, stream);
+}
+int sqllm_vecquant3matmul_spmv_nuq_perchannel_batched(const int32_t *rows, const int32_t *cols, const float *mat,
+                                                      const float *vec, float *mul, int num_rows, const int32_t *mat3,
+                                                      const float *lut, int height, int width, int batch, int vec_height,
+                                                      void *stream) {
+    return run12(3, vec, mat3, mul, lut, height, width, batch, vec_height, rows, cols, mat, num_rows, 0, 0, 0, 0, stream);
+}
+int sqllm_vecquant4matmul_spmv_nuq_perchannel_batched(const int32_t *rows, const int32_t *cols, const float *mat,
+                                                      const float *vec, float *mul, int num_rows, const int32_t *mat4,
+                                                      const float *lut, int height, int width, int batch, int vec_height,
+                                                      void *stream) {
+    return run12(4, vec, mat4, mul, lut, height, width, batch, vec_height, rows, cols, mat, num_rows, 0, 0, 0, 0, stream);
+}
+int sqllm_vecquant3matmul_spmv_hybrid_nuq_perchannel(const int32_t *rows, const int32_t *cols, const float *mat,
+                                                     const float *vec, const float *full_rows, const int32_t *fri,
+                                                     float *mul, int num_rows, const int32_t *mat3, const float *lut,
+                                                     int height, int width, int fr_height, int fr_width, void *stream) {
+    return run12(3, vec, mat3, mul, lut, height, width, 1, -1, rows, cols, mat, num_rows, full_rows, fri, fr_height, fr_width, stream);
+}
+int sqllm_vecquant4matmul_spmv_hybrid_nuq_perchannel(const int32_t *rows, const int32_t *cols, const float *mat,
+                                                     const float *vec, const float *full_rows, const int32_t *fri,
+                                                     float *mul, int num_rows, const int32_t *mat4, const float *lut,
+                                                     int height, int width, int fr_height, int fr_width, void *stream) {
+    return run12(4, vec, mat4, mul, lut, height, width, 1, -1, rows, cols, mat, num_rows, full_rows, fri, fr_height, fr_width, stream);
+}
+int sqllm_vecquant3matmul_spmv_hybrid_nuq_perchannel_batched(const int32_t *rows, const int32_t *cols, const float *mat,
+                                                             const float *vec, const float *full_rows, const int32_t *fri,
+                                                             float *mul, int num_rows, const int32_t *mat3, const float *lut,
+                                                             int height, int width, int fr_height, int fr_width, int batch,
+                                                             int vec_height, void *stream) {
+    return run12(3, vec, mat3, mul, lut, height, width, batch, vec_height, rows, cols, mat, num_rows, full_rows, fri, fr_height, fr_width, stream);
+}
+int sqllm_vecquant4matmul_spmv_hybrid_nuq_perchannel_batched(const int32_t *rows, const int32_t *cols, const float *mat,
+                                                             const float *vec, const float *full_rows, const int32_t *fri,
+                                                             float *mul, int num_rows, const int32_t *mat4, const float *lut,
+                                                             int height, int width, int fr_height, int fr_width, int batch,
+                                                             int vec_height, void *stream) {
+    return run12(4, vec, mat4, mul, lut, height, width, batch, vec_height, rows, cols, mat, num_rows, full_rows, fri, fr_height, fr_width, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol include/sqllm_b200.h
+declares, argument validation answers without touching a GPU, and the `quant_cuda` module carries the
+reference's 12 names (squeezellm/quant_cuda.cpp:258-269)."""
+import ctypes
+
+import pytest
+
+from util import Args, header_symbols, load_lib
+
+REFERENCE_SYMBOLS = [
+    "vecquant3matmul_nuq_perchannel", "vecquant4matmul_nuq_perchannel",
+    "vecquant3matmul_nuq_perchannel_batched", "vecquant4matmul_nuq_perchannel_batched",
+    "vecquant3matmul_spmv_nuq_perchannel", "vecquant4matmul_spmv_nuq_perchannel",
+    "vecquant3matmul_spmv_nuq_perchannel_batched", "vecquant4matmul_spmv_nuq_perchannel_batched",
+    "vecquant3matmul_spmv_hybrid_nuq_perchannel", "vecquant4matmul_spmv_hybrid_nuq_perchannel",
+    "vecquant3matmul_spmv_hybrid_nuq_perchannel_batched", "vecquant4matmul_spmv_hybrid_nuq_perchannel_batched",
+]
+
+
+def test_library_exports_every_declared_symbol():
+    lib = load_lib()
+    syms = header_symbols()
+    assert len(syms) >= 12 + 6
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/sqllm_b200.h but not exported"
+    for s in REFERENCE_SYMBOLS:
+        assert "sqllm_" + s in syms
+
+
+def test_abi_version_and_error_string():
+    lib = load_lib()
+    assert lib.sqllm_abi_version() == 1
+    assert isinstance(lib.sqllm_last_error(), bytes)
+
+
+@pytest.mark.parametrize("field,value,frag", [("bits", 5, b"bits"), ("in_features", 100, b"in_features"),
+                                              ("out_features", 6, b"out_features")])
+def test_argument_validation_without_gpu(field, value, frag):
+    lib = load_lib()
+    a = Args(bits=4, in_features=128, out_features=128, batch=1, qweight=16, lookup_table=16, vec=16, mul=16)
+    setattr(a, field, value)
+    rc = lib.sqllm_lutgemv(ctypes.byref(a), None)
+    assert rc == -1  # SQLLM_EINVAL
+    assert frag in lib.sqllm_last_error()
+
+
+def test_null_and_misaligned_pointers_rejected():
+    lib = load_lib()
+    a = Args(bits=4, in_features=128, out_features=128, batch=1, qweight=0, lookup_table=16, vec=16, mul=16)
+    assert lib.sqllm_lutgemv(ctypes.byref(a), None) == -1
+    a.qweight = 20  # not 16-byte aligned
+    assert lib.sqllm_lutgemv(ctypes.byref(a), None) == -1
+    assert b"aligned" in lib.sqllm_last_error()
+    assert lib.sqllm_lutgemv(None, None) == -1
+
+
+def test_reference_launcher_shape_checks():
+    lib = load_lib()
+    # height must be a multiple of bits (height = in/32*bits)
+    assert lib.sqllm_vecquant3matmul_nuq_perchannel(16, 16, 16, 16, 13, 128, None) == -1
+    # batched: vec_height must equal the in_features implied by the packed matrix
+    assert lib.sqllm_vecquant4matmul_nuq_perchannel_batched(16, 16, 16, 16, 16, 128, 2, 64, None) == -1
+    assert b"features" in lib.sqllm_last_error()
+
+
+def test_quant_cuda_module_has_the_reference_names():
+    from squeezellm_b200.quant import quant_cuda
+    for s in REFERENCE_SYMBOLS:
+        assert callable(getattr(quant_cuda, s))
+    assert not any("balanced" in n for n in dir(quant_cuda))  # absent in the reference build too
+    assert quant_cuda.abi_version() == 1
+
+
+def test_quant_cuda_rejects_cpu_tensors_loudly():
+    """No CPU fallback: calling the extension with host tensors raises instead of computing something."""
+    import torch
+    from squeezellm_b200.quant import quant_cuda
+    x = torch.zeros(128); q = torch.zeros((16, 128), dtype=torch.int32); y = torch.zeros(128); lut = torch.zeros((128, 16))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        quant_cuda.vecquant4matmul_nuq_perchannel(x, q, y, lut)
+    with pytest.raises(RuntimeError):
+        quant_cuda.lutgemv_fused(x, q, lut, 4)

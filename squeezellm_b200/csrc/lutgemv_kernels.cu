@@ -44,6 +44,8 @@ constexpr int PF4 = 4;                // 128-bit loads in flight per lane, 4-bit
 constexpr int PF3 = 2;                // 3-row groups in flight per lane, 3-bit path
 constexpr int SROWS_LD = 68;          // padded row-pointer slice per segment (65 used)
 constexpr int MAX_TOPX_FUSED = 128;
+constexpr int MAX_STRIPS = 16320;          // per-strip tickets in the workspace header (out_features <= 1,044,480)
+constexpr size_t WS_HEADER = 65536;
 
 struct Params {
     const uint32_t *qw;
@@ -505,6 +507,7 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
                     for (int k = kb; k < ke; ++k, fr += p.topX) a += __ldg(fr) * xs[k];
                     if (FUSED) {
                         p.ws_hyb[(size_t)blockIdx.x * p.topX + j] = a;
+                        __threadfence();
                     } else {
                         const int c = __ldg(p.fri + j);
                         if (c >= 0 && c < N) atomicAdd(reinterpret_cast<float *>(p.out) + c, a);
@@ -522,10 +525,12 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
                 if (last) {
                     __threadfence();
                     if (lane == 0) *p.ws_hyb_cnt = 0;
-                    for (int j = lane; j < p.topX; j += 32) {
+                    for (int j = 0; j < p.topX; ++j) {  // lanes stride over contributors, fixed xor tree -> deterministic
                         float t = 0.f;
-                        for (int b = 0; b < p.hc; ++b) t += ldcg_f32(p.ws_hyb + (size_t)b * p.topX + j);
-                        hyb_tot[j] = t;
+#pragma unroll 4
+                        for (int b = lane; b < p.hc; b += 32) t += ldcg_f32(p.ws_hyb + (size_t)b * p.topX + j);
+                        t = warp_sum(t);
+                        if (lane == 0) hyb_tot[j] = t;
                     }
                     __syncwarp();
                     // hand one "hybrid slot" vector to every strip that owns a dense-row output channel
@@ -551,6 +556,7 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
                         float *slot = p.ws_part + ((size_t)strip * (p.maxc + 1) + p.maxc) * STRIP;
                         slot[lane] = v0;
                         slot[lane + 32] = v1;
+                        __threadfence();
                         __syncwarp();
                         const int first = (int)(((long long)strip * R) / p.chunk);
                         const int lastc = (int)((((long long)strip + 1) * R - 1) / p.chunk);
@@ -608,6 +614,7 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
                 }
             } else {
                 p.ws_part[((size_t)strip * (p.maxc + 1) + slot) * STRIP + c] = tot;
+                __threadfence();  // each writer publishes its own partial before the ticket is taken
             }
         }
         // ticket: 64 threads (2 warps) per segment; sync them with a named barrier per segment
@@ -733,10 +740,12 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &
         pl.hrows = (K + hc - 1) / hc;
         pl.hc = (K + pl.hrows - 1) / pl.hrows;
     }
-    size_t off = 0;
-    pl.ws_cnt_off = off; off += (size_t)pl.strips * 4;
-    pl.ws_hybcnt_off = off; off += 4;
-    off = (off + 255) & ~(size_t)255;
+    // Fixed header: [0,4) dense-row ticket, [256, 256+4*MAX_STRIPS) per-strip tickets.  Tickets must never
+    // share bytes with data regions of ANY shape (the workspace is reused across layers of different sizes).
+    if (pl.strips > MAX_STRIPS) return fail(SQLLM_EINVAL, "out_features=%d exceeds the %d-strip workspace header", N, MAX_STRIPS);
+    size_t off = WS_HEADER;
+    pl.ws_hybcnt_off = 0;
+    pl.ws_cnt_off = 256;
     pl.ws_hyb_off = off; off += (size_t)pl.hc * (topX > 0 ? topX : 0) * 4;
     off = (off + 255) & ~(size_t)255;
     pl.ws_part_off = off; off += (size_t)pl.strips * (pl.maxc + 1) * STRIP * 4;
@@ -751,7 +760,6 @@ int check_common(const sqllm_lutgemv_args *a) {
     if (a->out_features <= 0 || a->out_features % 4) return fail(SQLLM_EINVAL, "out_features=%d must be a positive multiple of 4", a->out_features);
     if (!a->qweight || !a->lookup_table) return fail(SQLLM_EINVAL, "qweight / lookup_table must not be null");
     if (reinterpret_cast<uintptr_t>(a->qweight) & 15) return fail(SQLLM_EINVAL, "qweight must be 16-byte aligned");
-    if (a->rows && (!a->cols || !a->vals)) return fail(SQLLM_EINVAL, "rows given without cols/vals");
     if (a->topX < 0) return fail(SQLLM_EINVAL, "topX < 0");
     if (a->full_rows && a->topX > 0 && !a->full_row_indices) return fail(SQLLM_EINVAL, "full_rows given without full_row_indices");
     return SQLLM_OK;

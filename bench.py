@@ -1,0 +1,419 @@
+#!/usr/bin/env python3
+"""bench.py - BASELINE.json's metric on BASELINE.json's config: LLaMA-7B w4-s45 decode tokens/s at batch 1
+(QuantLinear layers), plus the per-layer HBM roofline fraction.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload llama7b-w4-s45] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one decode token's pass over the hot path: the 7 QuantLinearLUT matvecs (q, k, v, o, gate, up, down) of
+each of the model's decoder layers, in model order, chained through their real shapes (x -> q,k,v ; v -> o ; o -> gate,up ;
+gate -> down -> next layer's x), on synthetic random-init weights in the reference's buffer format (distinct per layer:
+3.6 GB per token for 7B w4-s45, far beyond the 126 MB L2, so every step streams from HBM).  Attention, norms, rotary,
+lm_head and the KV cache are NOT part of the step (they are not on the path this repo replaces) and that is stated in
+`config`.  As `llama.py --include_sparse` always runs (llama.py:301-306), sparse layers use the hybrid symbol with
+topX=10 dense rows that are zero (a checkpoint without them, llama.py:182).
+
+  value  : tokens/s, device-timed, inputs resident in HBM, one CUDA-graph replay per step.
+  e2e    : same metric through the public API (squeezellm_b200.runtime.GraphedDecodeStep over QuantLinearLUT.forward)
+           with the token's activation coming from pinned host memory and the result read back every step.
+  roofline: algorithmic bytes of all launches of the step / step time vs the measured HBM copy bandwidth.
+  cpu_baseline / --impl reference: the reference has no CPU path; this is the restatement north_star names
+           (unpack -> LUT gather -> fp16 W -> torch.matmul, + CSR + dense rows) on the box's host cores, on ONE decoder
+           layer per step (bounded sample), extrapolated to the model's layer count.
+  N > 1  : every QuantLinear is column-sharded N ways (qweight[:, c0:c1], LUT rows, CSR rows re-based) and the output
+           vector is summed with one NCCL all-reduce per matvec (north_star); "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: hidden, ffn, layers, bits, sparsity, topX
+    "llama7b-w4-s45": dict(hidden=4096, ffn=11008, layers=32, bits=4, sparsity=0.0045, topX=10),
+    "llama7b-w4-s0": dict(hidden=4096, ffn=11008, layers=32, bits=4, sparsity=0.0, topX=0),
+    "llama7b-w3-s45": dict(hidden=4096, ffn=11008, layers=32, bits=3, sparsity=0.0045, topX=10),
+    "llama13b-w4-s5": dict(hidden=5120, ffn=13824, layers=40, bits=4, sparsity=0.0005, topX=10),
+    "llama65b-w3-s45": dict(hidden=8192, ffn=22016, layers=80, bits=3, sparsity=0.0045, topX=10),
+}
+MATS = [("q_proj", "hidden", "hidden"), ("k_proj", "hidden", "hidden"), ("v_proj", "hidden", "hidden"),
+        ("o_proj", "hidden", "hidden"), ("gate_proj", "hidden", "ffn"), ("up_proj", "hidden", "ffn"),
+        ("down_proj", "ffn", "hidden")]
+
+
+def alg_bytes(bits, K, N, nnz, topx):
+    """packed words + fp32 LUT + fp32 x + fp32 y (+ CSR cols/vals/rows) (+ dense rows)."""
+    b = K // 32 * bits * N * 4 + N * (2 ** bits) * 4 + K * 4 + N * 4
+    if nnz:
+        b += nnz * 8 + (N + 1) * 4
+    if topx:
+        b += K * topx * 4 + topx * 4
+    return b
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, bf16 copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# synthetic model in the reference's buffer format, generated on the device
+# ------------------------------------------------------------------------------------------------------------------
+def synth_matrix(bits, K, N, sparsity, topx, gen, dev, c0=0, c1=None):
+    """Buffers of one QuantLinearLUT [K -> N]; columns [c0, c1) only (column shard) if given."""
+    c1 = N if c1 is None else c1
+    n = c1 - c0
+    d = {}
+    d["qweight"] = torch.randint(-2**31, 2**31 - 1, (K // 32 * bits, n), dtype=torch.int64, device=dev, generator=gen).to(torch.int32)
+    # per-channel sorted centroids, scaled so that a matvec keeps |x| ~ O(1) through 224 chained layers
+    d["lookup_table"] = torch.sort(torch.randn((n, 2 ** bits), device=dev, generator=gen) * (K ** -0.5), dim=1).values.contiguous()
+    nnz = int(round(sparsity * K * n))
+    if nnz:
+        counts = torch.bincount(torch.randint(0, n, (nnz,), device=dev, generator=gen), minlength=n)
+        rows = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        rows[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        d["rows"] = rows
+        d["cols"] = torch.randint(0, K, (nnz,), device=dev, generator=gen).to(torch.int32)
+        d["vals"] = torch.randn(nnz, device=dev, generator=gen) * (0.5 * K ** -0.5)
+    if topx and nnz:
+        d["full_rows"] = torch.zeros((K, topx), device=dev)
+        d["full_row_indices"] = torch.zeros(topx, dtype=torch.int32, device=dev)
+    return d, nnz
+
+
+def build_model(cfg, dev, rank, world, seed=0):
+    from squeezellm_b200.quant import QuantLinearLUT
+    gen = torch.Generator(device=dev).manual_seed(seed + 1000 * rank)
+    layers, nbytes, nlaunch = [], 0, 0
+    for li in range(cfg["layers"]):
+        mods = {}
+        for name, kin, kout in MATS:
+            K, N = cfg[kin], cfg[kout]
+            assert N % (4 * world) == 0, f"{name}: out_features {N} does not split into {world} shards of a multiple of 4"
+            w = N // world
+            d, nnz = synth_matrix(cfg["bits"], K, N, cfg["sparsity"], cfg["topX"], gen, dev, rank * w, (rank + 1) * w)
+            m = QuantLinearLUT(cfg["bits"], K, w, False, include_sparse=nnz > 0, numvals=nnz, topX=cfg["topX"] if nnz else 0)
+            for k, v in d.items():
+                setattr(m, k, v)  # registered buffers: assignment keeps them buffers
+            mods[name] = m
+            nbytes += alg_bytes(cfg["bits"], K, w, nnz, cfg["topX"] if nnz else 0)
+            nlaunch += 1
+        layers.append(mods)
+    return layers, nbytes, nlaunch
+
+
+def make_step(layers, world, hidden_dtype=torch.float16):
+    """x [hidden] -> x' [hidden]: the 7 matvecs per decoder layer in model order (see module docstring)."""
+    if world == 1:
+        def step(x):
+            for L in layers:
+                L["q_proj"](x)
+                L["k_proj"](x)
+                v = L["v_proj"](x)
+                o = L["o_proj"](v)
+                g = L["gate_proj"](o)
+                L["up_proj"](o)
+                x = L["down_proj"](g)
+            return x
+        return step
+
+    import torch.distributed as dist
+    rank = dist.get_rank()
+
+    def sharded(m, x, full):
+        """column shard -> its slice of a zero-padded full-length vector -> one all-reduce (north_star)."""
+        w = m.outfeatures
+        full.zero_()
+        full[rank * w:(rank + 1) * w] = m(x)
+        dist.all_reduce(full)
+        return full
+
+    bufs = {}
+
+    def buf(name, n, dev):
+        if name not in bufs:
+            bufs[name] = torch.zeros(n, dtype=hidden_dtype, device=dev)
+        return bufs[name]
+
+    def step(x):
+        for L in layers:
+            for name in ("q_proj", "k_proj"):
+                sharded(L[name], x, buf(name, L[name].outfeatures * world, x.device))
+            v = sharded(L["v_proj"], x, buf("v", L["v_proj"].outfeatures * world, x.device))
+            o = sharded(L["o_proj"], v, buf("o", L["o_proj"].outfeatures * world, x.device))
+            g = sharded(L["gate_proj"], o, buf("g", L["gate_proj"].outfeatures * world, x.device))
+            sharded(L["up_proj"], o, buf("u", L["up_proj"].outfeatures * world, x.device))
+            x = sharded(L["down_proj"], g, buf("d", L["down_proj"].outfeatures * world, x.device)).clone()
+        return x
+    return step
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) - bench.py's only use of oracle/
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_layer_sample(cfg, reps, seed=0):
+    """Seconds per decoder layer for the 'dequant-to-fp16 + torch.matmul' CPU path, timed on host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    mats = []
+    for i, (name, kin, kout) in enumerate(MATS):
+        L = orc.make_layer(cfg["bits"], cfg[kin], cfg[kout], sparsity=cfg["sparsity"], topX=cfg["topX"] if cfg["sparsity"] else 0, seed=seed + i)
+        mats.append((L, orc.make_vec(cfg[kin], seed=i)))
+    times, fused_times = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for L, x in mats:
+            orc.cpu_dequant_matmul(L, x, compute_dtype="float16")
+        times.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for L, x in mats:
+            orc.forward_f32_blocked(L, x)
+        fused_times.append(time.perf_counter() - t0)
+    return times, fused_times, orc.threads()
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    times, fused, thr = cpu_layer_sample(cfg, args.warmup + args.steps)
+    t = times[args.warmup:]
+    per_tok = statistics.mean(t) * cfg["layers"]
+    val = 1.0 / per_tok
+    fused_val = 1.0 / (statistics.mean(fused[args.warmup:]) * cfg["layers"])
+    sample = f"1 of {cfg['layers']} decoder layers (7 matvecs) per step, fp16 dequant + torch.matmul + CSR + dense rows; x{cfg['layers']} extrapolated"
+    out = {"metric": "decode tokens/s at batch=1 (QuantLinear layers)", "value": val, "unit": "tokens/s", "impl": "reference",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_tok * 1e3, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f16 weights x f16 activations (torch CPU matmul)", "data": "synthetic",
+           "config": {"workload": args.workload, "batch": 1, "note": "reference has no CPU path; restatement named by north_star"},
+           "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                            "fused_lookup_gemv_port_tokens_per_s": fused_val, "fused_port_threads": thr, "host_cpus": os.cpu_count()},
+           "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="llama7b-w4-s45", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug only; the JSON says so)")
+    args = ap.parse_args()
+    cfg = dict(WORKLOADS[args.workload])
+    if args.layers:
+        cfg["layers"] = args.layers
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run for N>1)"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback for the product path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    layers, nbytes, nlaunch = build_model(cfg, dev, rank, world)
+    step = make_step(layers, world)
+    x0 = torch.randn(cfg["hidden"], device=dev).half()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from squeezellm_b200.runtime import GraphedDecodeStep
+    graphed = True
+    try:
+        runner = GraphedDecodeStep(step, x0, warmup=3)
+    except Exception as e:  # e.g. NCCL refusing capture: fall back to eager launches, and say so
+        if world == 1:
+            raise
+        graphed, runner = False, None
+        print(f"[bench] graph capture failed on rank {rank}: {e}; timing eager", file=sys.stderr)
+        torch.cuda.synchronize()
+
+    def one_step():
+        if graphed:
+            runner.replay()
+        else:
+            step(x0)
+
+    # ---- device-resident timing --------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        one_step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end from host memory through the public API ---------------------------------------------------
+    xh = torch.randn(cfg["hidden"]).half().pin_memory()
+    e2e_ms = None
+    if graphed:
+        for _ in range(args.warmup):
+            runner(xh)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            runner(xh)
+        ev1.record()
+        barrier()
+        e2e_ms = ev0.elapsed_time(ev1)
+    else:
+        yh = torch.empty(cfg["hidden"], dtype=torch.float16).pin_memory()
+        for _ in range(args.warmup):
+            yh.copy_(step(xh.to(dev, non_blocking=True)))
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            yh.copy_(step(xh.to(dev, non_blocking=True)))
+        ev1.record()
+        barrier()
+        e2e_ms = ev0.elapsed_time(ev1)
+
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+        tot = torch.tensor([float(nbytes)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tot)
+        nbytes_all = tot.item()
+    else:
+        nbytes_all = float(nbytes)
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms / args.steps
+    tok_s = 1e3 / ms_step
+    e2e_tok_s = 1e3 / (e2e_ms / args.steps)
+    peak, peak_src = peaks()
+    achieved = nbytes / (ms_step * 1e-3) / 1e9  # per GPU: this rank's bytes over the step time
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    out = {
+        "metric": "LLaMA-7B w4-s45 decode tokens/s at batch=1 (QuantLinear layers); per-layer HBM GB/s vs peak" if args.workload == "llama7b-w4-s45"
+                  else f"{args.workload} decode tokens/s at batch=1 (QuantLinear layers)",
+        "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 accumulate (fp32 LUT x fp16->fp32 activations, fp16 outputs)", "data": "synthetic",
+        "config": {"workload": args.workload, "batch": 1, "layers": cfg["layers"], "hidden": cfg["hidden"], "ffn": cfg["ffn"], "bits": cfg["bits"],
+                   "sparsity": cfg["sparsity"], "topX": cfg["topX"], "matvecs_per_step": nlaunch,
+                   "scope": "QuantLinearLUT matvecs only; attention/norms/lm_head/KV cache excluded",
+                   "l2": f"{nbytes_all / 1e9:.2f} GB of distinct weights per step >> 126 MB L2 (inputs larger than L2)",
+                   "parallelism": "single GPU" if world == 1 else f"column-sharded x{world} + NCCL all-reduce per matvec",
+                   "launch": "one CUDA-graph replay per step" if graphed else "eager launches (graph capture unavailable)",
+                   "layers_overridden": bool(args.layers)},
+        "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": cfg["hidden"] * 2, "d2h_bytes_per_step": cfg["hidden"] * 2,
+                "api": "squeezellm_b200.runtime.GraphedDecodeStep over QuantLinearLUT.forward" if graphed else "QuantLinearLUT.forward eager"},
+        "gpu_launches": nlaunch * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "kernel": f"lutgemv_kernel<{cfg['bits']},fused>",
+                     "algorithmic_bytes_per_step_per_gpu": nbytes, "frac_of_nominal_8000": achieved / 8000.0},
+    }
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        times, fused, thr = cpu_layer_sample(cfg, 2)
+        per_tok = min(times) * cfg["layers"]
+        out["cpu_baseline"] = {"value": 1.0 / per_tok, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"1 of {cfg['layers']} decoder layers (7 matvecs), best of 2, fp16 dequant + torch.matmul (+CSR, dense rows), x{cfg['layers']}",
+                               "fused_lookup_gemv_port_tokens_per_s": 1.0 / (min(fused) * cfg["layers"]), "fused_port_threads": thr,
+                               "host_cpus": os.cpu_count()}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

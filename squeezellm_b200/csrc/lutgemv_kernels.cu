@@ -7,44 +7,50 @@
 // and the 12 host launchers (:132-738), behind the C ABI of include/sqllm_b200.h.
 //
 // Design (DESIGN.md has the full story and the measurements):
-//   * ONE persistent launch per GEMV.  The [units x strips] iteration space (unit = one packed
-//     row for 4-bit, one 3-row / 32-input group for 3-bit; strip = 64 output columns) is flattened
-//     strip-major and cut into equal contiguous chunks, one per CTA (stream-K), so all SMs get the
-//     same number of bytes whatever the shape.  A CTA touches at most MAXSEG strips.
-//   * Each CTA stages, once: x (fp32) and the LUTs of its <= MAXSEG strips, transposed to
-//     [value][column-slot] so that every lane owns one shared-memory bank -> conflict-free gathers.
-//   * 8 "dense" warps stream the packed words with 128-bit read-only loads, register-prefetched
-//     PREFETCH deep, and turn every 4-bit index into an LDS address with a single PRMT (the table
-//     is 4 KB aligned, so address = {table_hi16, nibble|table_bits12-15, slot*4}); products are
-//     accumulated with packed fma.rn.f32x2.  No tensor cores: this is a gather-bound GEMV.
-//   * 1 "sparse" warp per CTA runs concurrently: it stages the CSR rows of the strips this CTA
-//     owns with cp.async and reduces them deterministically, and takes a slice of the topX dense
-//     rows.  Everything lands in the same fp32 accumulator before a single flush.
-//   * Flush: accumulate mode (the reference's 12 symbols; `mul` pre-filled by the caller) uses one
-//     red.add.f32 per (CTA, column).  Fused mode (QuantLinearLUT.forward fast path) writes partials to
-//     a workspace and the last-arriving CTA of each strip (atomic ticket, no spinning) sums them in
+//   * ONE launch per GEMV.  The [units x strips] iteration space (unit = one packed row for 4-bit,
+//     one 3-row / 32-input group for 3-bit; strip = 64 output columns) is flattened strip-major and
+//     cut into equal contiguous chunks, one per CTA (stream-K): every SM gets the same number of
+//     bytes whatever the shape.  A CTA touches at most MAXSEG strips.
+//   * Warp roles (10 warps): 8 consumers, 1 TMA producer, 1 sparse warp.
+//       - producer: streams the CTA's packed rows with cp.async.bulk (TMA, L2 evict-first) into an
+//         mbarrier-guarded ring of NSTAGE stages (16 units each); it starts before the programmatic
+//         dependency on the previous kernel is resolved (PDL), so weight traffic of GEMV n+1 overlaps
+//         the tail of GEMV n.
+//       - consumers: wait on a stage, pull their 128-bit word-quads into registers, release the
+//         stage, and turn every 4-bit index into an LDS address with a single PRMT (the per-strip
+//         LUT is staged transposed [value][column-slot] in a 4 KB aligned table so that every lane
+//         owns one shared-memory bank: conflict-free gathers); products go into packed
+//         fma.rn.f32x2 accumulators.  No tensor cores: this is a gather-bound GEMV.
+//       - sparse warp: stages the CSR rows of the strips this CTA owns with cp.async, reduces them
+//         deterministically, and takes a slice of the topX dense rows.
+//   * Only the slice of x a CTA needs is staged (fp32, converted from fp16 on the way in).
+//   * Flush: accumulate mode (the reference's 12 symbols; `mul` pre-filled by the caller) issues one
+//     red.add.f32 per (CTA, column).  Fused mode (QuantLinearLUT.forward fast path) writes partials
+//     to a workspace; the last-arriving CTA of each strip (atomic ticket, no spinning) sums them in
 //     fixed order, adds bias, converts and stores -> deterministic, no pre-zeroed output.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
-#include <stdint.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sqllm_b200.h"
 
 namespace {
 
-constexpr int NW = 8;                 // dense warps per CTA
-constexpr int THREADS = (NW + 1) * 32;  // + 1 sparse warp
-constexpr int MAXSEG = 4;             // strips a CTA may touch
-constexpr int STRIP = 64;             // output columns per strip (16 lanes x 4 columns)
-constexpr int CSR_CH = 2048;          // CSR elements staged per chunk
-constexpr int PF4 = 4;                // 128-bit loads in flight per lane, 4-bit path
-constexpr int PF3 = 2;                // 3-row groups in flight per lane, 3-bit path
-constexpr int SROWS_LD = 68;          // padded row-pointer slice per segment (65 used)
+constexpr int NW = 8;                     // consumer warps per CTA
+constexpr int WARP_PRODUCER = NW;         // warp index of the TMA producer
+constexpr int WARP_SPARSE = NW + 1;       // warp index of the CSR / dense-row warp
+constexpr int THREADS = (NW + 2) * 32;
+constexpr int MAXSEG = 4;                 // strips a CTA may touch
+constexpr int STRIP = 64;                 // output columns per strip (16 lanes x 4 columns)
+constexpr int SU = 2 * NW;                // units per pipeline stage (one pair per consumer warp)
+constexpr int CSR_CH = 1024;              // CSR elements staged per chunk
+constexpr int SROWS_LD = 68;              // padded row-pointer slice per segment (65 used)
 constexpr int MAX_TOPX_FUSED = 128;
-constexpr int MAX_STRIPS = 16320;          // per-strip tickets in the workspace header (out_features <= 1,044,480)
+constexpr int MAX_STRIPS = 16320;         // per-strip tickets in the workspace header (out_features <= 1,044,480)
 constexpr size_t WS_HEADER = 65536;
 
 struct Params {
@@ -59,33 +65,46 @@ struct Params {
     const int *fri;
     int topX;
     int K, N;
-    int R;       // units per strip
+    int R;        // units per strip
     int strips;
-    int T;       // strips * R
-    int chunk;   // units per CTA (even)
-    int hc;      // CTAs that take a slice of the dense rows
-    int hrows;   // k-rows per such CTA
+    int T;        // strips * R
+    int chunk;    // units per CTA (even)
+    int maxseg;   // strips a CTA of this launch can touch (sizes the LUT tables)
+    int x_direct; // 1: x staged at its natural index (CTA covers whole strips), 0: compact, indexed by unit offset
+    int xfloats;  // floats in the x staging buffer
+    int hc;       // CTAs that take a slice of the dense rows
+    int hrows;    // k-rows per such CTA
     int x_is_half, y_is_half;
-    int maxc;    // max dense contributors per strip (fused)
+    int maxc;     // max dense contributors per strip (fused)
     float *ws_part;   // [strips][maxc+1][64]
     int *ws_cnt;      // [strips]
     float *ws_hyb;    // [hc][topX]
     int *ws_hyb_cnt;  // [1]
-    int has_csr_stage;
+    int has_csr;
 };
 
-// ---- shared memory carve-up (offsets from a 4 KB aligned base) -----------------------------------
+// ---- per-bit-width constants and the shared memory carve-up (offsets from a 4 KB aligned base) ---
 template <int BITS>
-struct Smem {
-    static constexpr int TAB = (1 << BITS) * STRIP * 4;  // 4096 (w4) / 2048 (w3) bytes per segment
-    static constexpr int off_tab = 0;
-    static constexpr int off_part = off_tab + MAXSEG * TAB;                // float [MAXSEG][NW][64]
-    static constexpr int off_csr = off_part + MAXSEG * NW * STRIP * 4;     // float [MAXSEG][64]
-    static constexpr int off_srows = off_csr + MAXSEG * STRIP * 4;         // int   [MAXSEG][SROWS_LD]
-    static constexpr int off_misc = off_srows + MAXSEG * SROWS_LD * 4;     // int   [16] + float[MAX_TOPX_FUSED]
-    static constexpr int off_x = off_misc + 64 + MAX_TOPX_FUSED * 4;       // float [K]
-    __host__ __device__ static int off_stage(int K) { return off_x + K * 4; }  // int[CSR_CH] + float[CSR_CH]
-    __host__ __device__ static int total(int K, bool stage) { return 4096 + off_stage(K) + (stage ? CSR_CH * 8 : 0); }
+struct Cfg {
+    static constexpr int L = 1 << BITS;
+    static constexpr int TAB = L * STRIP * 4;              // 4096 (w4) / 2048 (w3) bytes per strip table
+    static constexpr int ROWS_PER_UNIT = BITS == 4 ? 1 : 3;
+    static constexpr int XU = BITS == 4 ? 8 : 32;          // inputs per unit
+    static constexpr int UNIT_BYTES = ROWS_PER_UNIT * STRIP * 4;
+    static constexpr int STAGE_BYTES = SU * UNIT_BYTES;    // 4 KB (w4) / 12 KB (w3)
+    static constexpr int NSTAGE = BITS == 4 ? 6 : 3;
+    // layout: [tables maxseg*TAB][stages][part][csr_acc][srows][misc][x][csr stage]
+    __host__ __device__ static int off_stage(int maxseg) { return maxseg * TAB; }
+    __host__ __device__ static int off_part(int maxseg) { return off_stage(maxseg) + NSTAGE * STAGE_BYTES; }
+    __host__ __device__ static int off_csr(int maxseg) { return off_part(maxseg) + MAXSEG * NW * STRIP * 4; }
+    __host__ __device__ static int off_srows(int maxseg) { return off_csr(maxseg) + MAXSEG * STRIP * 4; }
+    __host__ __device__ static int off_misc(int maxseg) { return off_srows(maxseg) + MAXSEG * SROWS_LD * 4; }
+    // misc: 16 mbarriers (128 B) + 16 ints (64 B) + float[MAX_TOPX_FUSED]
+    __host__ __device__ static int off_x(int maxseg) { return off_misc(maxseg) + 128 + 64 + MAX_TOPX_FUSED * 4; }
+    __host__ __device__ static int off_cstage(int maxseg, int xfloats) { return off_x(maxseg) + ((xfloats * 4 + 15) & ~15); }
+    __host__ __device__ static int total(int maxseg, int xfloats, bool csr) {
+        return 4096 + off_cstage(maxseg, xfloats) + (csr ? CSR_CH * 8 : 0);
+    }
 };
 
 // ---- small PTX helpers -------------------------------------------------------------------------
@@ -100,10 +119,9 @@ __device__ __forceinline__ float4 lds_v4(uint32_t a) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
-__device__ __forceinline__ uint4 ldg_stream(const void *p) {  // read-once weights: bypass L1 allocation
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
@@ -134,20 +152,50 @@ __device__ __forceinline__ float warp_sum(float v) {  // fixed xor tree -> deter
 }
 __device__ __forceinline__ float ldcg_f32(const float *p) { return __ldcg(p); }
 
-// Iterator over the units a dense warp processes: pairs of units (one per half-warp), round-robin.
+// mbarrier / TMA bulk copy / PDL
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Maps a unit offset `o` (from the CTA's first unit) to (segment, unit-in-strip); advanced incrementally.
 struct UnitIt {
-    int o;    // offset of the pair from the CTA's first unit
-    int rr;   // unit index inside the strip (even)
-    int seg;  // local segment
-    __device__ __forceinline__ void init(int warp, int r0, int R) {
-        o = 2 * warp;
-        rr = r0 + o;
+    int o, rr, seg;
+    __device__ __forceinline__ void init(int first, int r0, int R) {
+        o = first;
+        rr = r0 + first;
         seg = 0;
         while (rr >= R) { rr -= R; ++seg; }
     }
-    __device__ __forceinline__ void next(int R) {
-        o += 2 * NW;
-        rr += 2 * NW;
+    __device__ __forceinline__ void advance(int step, int R) {
+        o += step;
+        rr += step;
         while (rr >= R) { rr -= R; ++seg; }
     }
 };
@@ -217,10 +265,16 @@ __device__ __forceinline__ void consume3_col(const uint32_t w0, const uint32_t w
     LK3(a, fld<26>(w2), lsv); LK3(b, fld<29>(w2), lsv); ffma2(acc, pack2(a, b), xp[15]);
 }
 
-struct Grp3 { uint4 a, b, c; };
+template <int BITS> struct Words;
+template <> struct Words<4> { uint4 a; };
+template <> struct Words<3> { uint4 a, b, c; };
 
-__device__ __forceinline__ void consume3(const Grp3 &g, const int jsel, const uint32_t (&ls)[4], const uint32_t xaddr,
-                                         uint64_t (&acc)[4]) {
+__device__ __forceinline__ void consume(const Words<4> &g, const int jsel, const uint32_t (&ls)[4], const uint32_t segc,
+                                        const uint32_t xaddr, uint64_t (&acc)[4]) {
+    consume4(g.a, jsel, ls, segc, xaddr, acc);
+}
+__device__ __forceinline__ void consume(const Words<3> &g, const int jsel, const uint32_t (&ls)[4], const uint32_t,
+                                        const uint32_t xaddr, uint64_t (&acc)[4]) {
     uint64_t xp[16];
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
@@ -233,6 +287,12 @@ __device__ __forceinline__ void consume3(const Grp3 &g, const int jsel, const ui
     const uint32_t c[4] = {jsel ? g.c.y : g.c.x, jsel ? g.c.x : g.c.y, jsel ? g.c.w : g.c.z, jsel ? g.c.z : g.c.w};
 #pragma unroll
     for (int t = 0; t < 4; ++t) consume3_col(a[t], b[t], c[t], ls[t], xp, acc[t]);
+}
+__device__ __forceinline__ void load_words(Words<4> &g, uint32_t unit_addr) { g.a = lds_u4(unit_addr); }
+__device__ __forceinline__ void load_words(Words<3> &g, uint32_t unit_addr) {
+    g.a = lds_u4(unit_addr);
+    g.b = lds_u4(unit_addr + STRIP * 4);
+    g.c = lds_u4(unit_addr + 2 * STRIP * 4);
 }
 
 // ---- per-column final reduction of a strip's workspace partials (fused mode) ----------------------
@@ -258,25 +318,259 @@ __device__ __forceinline__ bool strip_has_hybrid(const Params &p, int strip) {
     return h;
 }
 
+__device__ __forceinline__ float load_x(const Params &p, int k) {
+    return p.x_is_half ? __half2float(reinterpret_cast<const __half *>(p.x)[k]) : reinterpret_cast<const float *>(p.x)[k];
+}
+
+// =================================================================================================
+// Sparse warp: CSR outliers of the strips this CTA owns + a slice of the topX dense rows.
+// Everything that does not depend on the previous kernel (row pointers, cols/vals staging, the dense-row
+// values) is fetched BEFORE griddepcontrol.wait, so under PDL it overlaps the previous GEMV.
+// =================================================================================================
+template <int BITS, bool FUSED>
+__device__ __forceinline__ void sparse_warp(const Params &p, unsigned char *sm, const uint32_t sm_u32, const int lane,
+                                            const int nseg, const int s0, const int r0, float *csr_acc, int *srows,
+                                            float *hyb_tot) {
+    using C = Cfg<BITS>;
+    const int N = p.N, R = p.R;
+    for (int e = lane; e < MAXSEG * STRIP; e += 32) csr_acc[e] = 0.f;
+
+    // ---------------- phase A: static data ----------------
+    constexpr int HYB_R = 8;
+    float hfr[HYB_R];
+    const bool hyb_on = p.full_rows && (int)blockIdx.x < p.hc;
+    const bool hyb_multi = hyb_on && p.topX <= 16;  // several k-rows per warp step: lane = (row slot, column j)
+    int kb = 0, ke = 0, nsl = 1, rs = 0, hj = lane;
+    if (hyb_on) { kb = blockIdx.x * p.hrows; ke = min(p.K, kb + p.hrows); }
+    if (hyb_multi) {
+        nsl = 32 / p.topX;
+        rs = lane / p.topX;
+        hj = lane - rs * p.topX;
+#pragma unroll
+        for (int i = 0; i < HYB_R; ++i) {
+            const int k = kb + rs + nsl * i;
+            hfr[i] = (rs < nsl && k < ke) ? __ldg(p.full_rows + (size_t)k * p.topX + hj) : 0.f;
+        }
+    }
+    const int cso = C::off_cstage(p.maxseg, p.xfloats);
+    int *scols = reinterpret_cast<int *>(sm + cso);
+    float *svals = reinterpret_cast<float *>(sm + cso + CSR_CH * 4);
+    const uint32_t scols_u32 = sm_u32 + cso, svals_u32 = scols_u32 + CSR_CH * 4;
+    auto chunk_end = [&](const int *sr, int nc, int cb) {  // largest ce with sr[ce]-sr[cb] <= CSR_CH (at least cb+1)
+        int ce = cb + 1;
+        while (ce < nc && sr[ce + 1] - sr[cb] <= CSR_CH) ++ce;
+        return ce;
+    };
+    auto stage = [&](int base, int cnt) {
+        for (int e = lane; e < cnt; e += 32) {
+            cp_async4(scols_u32 + 4 * e, p.cols + base + e);
+            cp_async4(svals_u32 + 4 * e, p.vals + base + e);
+        }
+        cp_async_commit();
+    };
+    int fseg = -1;
+    if (p.rows) {
+        for (int seg = 0; seg < nseg; ++seg) {
+            const bool owner = (seg > 0) || (r0 == 0);
+            if (!owner) continue;
+            if (fseg < 0) fseg = seg;
+            const int c0 = (s0 + seg) * STRIP;
+            const int nc = min(STRIP, N - c0);
+            for (int t = lane; t <= nc; t += 32) srows[seg * SROWS_LD + t] = __ldg(p.rows + c0 + t);
+        }
+        __syncwarp();
+        if (fseg >= 0) {  // pre-stage the first chunk
+            const int nc = min(STRIP, N - (s0 + fseg) * STRIP);
+            const int *sr = srows + fseg * SROWS_LD;
+            const int ce = chunk_end(sr, nc, 0);
+            const int cnt = sr[ce] - sr[0];
+            if (cnt <= CSR_CH) stage(sr[0], cnt);
+        }
+    }
+
+    pdl_wait();
+
+    // ---------------- phase B: needs x (and, in fused mode, the workspace) ----------------
+    // (1) topX dense rows: CTA b < hc takes k-rows [kb, ke)
+    if (hyb_on) {
+        for (int jb = 0; jb < (hyb_multi ? 1 : p.topX); jb += 32) {
+            float a = 0.f;
+            int j;
+            if (hyb_multi) {
+                j = hj;
+#pragma unroll
+                for (int i = 0; i < HYB_R; ++i) {
+                    const int k = kb + rs + nsl * i;
+                    if (rs < nsl && k < ke) a += hfr[i] * load_x(p, k);
+                }
+                for (int k = kb + rs + nsl * HYB_R; rs < nsl && k < ke; k += nsl)
+                    a += __ldg(p.full_rows + (size_t)k * p.topX + hj) * load_x(p, k);
+                // fold the row slots onto slot 0 in fixed order
+                for (int sl = 1; sl < nsl; ++sl) {
+                    const float v = __shfl_sync(0xffffffffu, a, (hj + sl * p.topX) & 31);
+                    if (rs == 0) a += v;
+                }
+                if (rs != 0) j = p.topX;  // only slot 0 publishes
+            } else {
+                j = jb + lane;
+                if (j < p.topX) {
+                    const float *fr = p.full_rows + (size_t)kb * p.topX + j;
+#pragma unroll 8
+                    for (int k = kb; k < ke; ++k, fr += p.topX) a += __ldg(fr) * load_x(p, k);
+                }
+            }
+            if (j < p.topX) {
+                if (FUSED) {
+                    p.ws_hyb[(size_t)blockIdx.x * p.topX + j] = a;
+                    __threadfence();
+                } else {
+                    const int c = __ldg(p.fri + j);
+                    if (c >= 0 && c < N) atomicAdd(reinterpret_cast<float *>(p.out) + c, a);
+                }
+            }
+        }
+        if (FUSED) {
+            __syncwarp();
+            int last = 0;
+            if (lane == 0) {
+                __threadfence();
+                last = (atomicAdd(p.ws_hyb_cnt, 1) == p.hc - 1);
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence();
+                if (lane == 0) *p.ws_hyb_cnt = 0;
+                for (int j = 0; j < p.topX; ++j) {  // lanes stride over contributors, fixed xor tree -> deterministic
+                    float t = 0.f;
+#pragma unroll 4
+                    for (int b = lane; b < p.hc; b += 32) t += ldcg_f32(p.ws_hyb + (size_t)b * p.topX + j);
+                    t = warp_sum(t);
+                    if (lane == 0) hyb_tot[j] = t;
+                }
+                __syncwarp();
+                // hand one "hybrid slot" vector to every strip that owns a dense-row output channel
+                for (int j0 = 0; j0 < p.topX; ++j0) {
+                    const int cj0 = __ldg(p.fri + j0);
+                    if (cj0 < 0 || cj0 >= N) continue;
+                    const int strip = cj0 / STRIP;
+                    bool seen = false;
+                    for (int j = 0; j < j0; ++j) {
+                        const int cj = __ldg(p.fri + j);
+                        seen |= (cj >= 0 && cj < N && cj / STRIP == strip);
+                    }
+                    if (seen) continue;
+                    float v0 = 0.f, v1 = 0.f;  // columns lane, lane+32 of the strip
+                    for (int j = j0; j < p.topX; ++j) {
+                        const int cj = __ldg(p.fri + j);
+                        if (cj >= 0 && cj < N && cj / STRIP == strip) {
+                            const int cc = cj - strip * STRIP;
+                            if (cc == lane) v0 += hyb_tot[j];
+                            if (cc == lane + 32) v1 += hyb_tot[j];
+                        }
+                    }
+                    float *slot = p.ws_part + ((size_t)strip * (p.maxc + 1) + p.maxc) * STRIP;
+                    slot[lane] = v0;
+                    slot[lane + 32] = v1;
+                    __threadfence();
+                    __syncwarp();
+                    const int first = (int)(((long long)strip * R) / p.chunk);
+                    const int lastc = (int)((((long long)strip + 1) * R - 1) / p.chunk);
+                    const int nd = lastc - first + 1;
+                    int fin = 0;
+                    if (lane == 0) {
+                        __threadfence();
+                        fin = (atomicAdd(p.ws_cnt + strip, 1) == nd);  // nd dense contributors + this one
+                        if (fin) p.ws_cnt[strip] = 0;
+                    }
+                    fin = __shfl_sync(0xffffffffu, fin, 0);
+                    if (fin) {
+                        __threadfence();
+                        final_store(p, strip, lane, nd, true);
+                        final_store(p, strip, lane + 32, nd, true);
+                    }
+                }
+            }
+        }
+    }
+
+    // (2) CSR outliers: deterministic per-row sums into csr_acc (x gathered straight from global / L2)
+    if (p.rows) {
+        for (int seg = 0; seg < nseg; ++seg) {
+            const bool owner = (seg > 0) || (r0 == 0);
+            if (!owner) continue;
+            const int c0 = (s0 + seg) * STRIP;
+            const int nc = min(STRIP, N - c0);
+            const int *sr = srows + seg * SROWS_LD;
+            float *out = csr_acc + seg * STRIP;
+            int cb = 0;
+            while (cb < nc) {
+                const int base = sr[cb];
+                const int ce = chunk_end(sr, nc, cb);
+                const int cnt = sr[ce] - base;
+                if (cnt > CSR_CH) {  // one very long row: straight from global memory
+                    float a = 0.f;
+                    for (int e = base + lane; e < sr[cb + 1]; e += 32) a += __ldg(p.vals + e) * load_x(p, __ldg(p.cols + e));
+                    a = warp_sum(a);
+                    if (lane == 0) out[cb] = a;
+                    cb += 1;
+                    continue;
+                }
+                if (!(seg == fseg && cb == 0)) stage(base, cnt);
+                cp_async_wait_all();
+                __syncwarp();
+                // the product vals[e] * x[cols[e]] replaces vals[e] in place (independent gathers: full MLP)
+                for (int e = lane; e < cnt; e += 32) svals[e] *= load_x(p, scols[e]);
+                __syncwarp();
+                // pass 1: one lane per short row, sequential sum in storage order (two interleaved chains)
+                for (int c = cb + lane; c < ce; c += 32) {
+                    const int a0 = sr[c] - base, a1 = sr[c + 1] - base;
+                    if (a1 - a0 <= 64) {
+                        float ea = 0.f, eb = 0.f;
+                        int e = a0;
+                        for (; e + 1 < a1; e += 2) { ea += svals[e]; eb += svals[e + 1]; }
+                        if (e < a1) ea += svals[e];
+                        out[c] = ea + eb;
+                    }
+                }
+                // pass 2: the whole warp on each long row
+                for (int c = cb; c < ce; ++c) {
+                    const int a0 = sr[c] - base, a1 = sr[c + 1] - base;
+                    if (a1 - a0 > 64) {
+                        float a = 0.f;
+                        for (int e = a0 + lane; e < a1; e += 32) a += svals[e];
+                        a = warp_sum(a);
+                        if (lane == 0) out[c] = a;
+                    }
+                }
+                __syncwarp();
+                cb = ce;
+            }
+        }
+    }
+}
+
 // =================================================================================================
 // The kernel
 // =================================================================================================
 template <int BITS, bool FUSED>
 __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
-    using S = Smem<BITS>;
+    using C = Cfg<BITS>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 4095) & ~uintptr_t(4095));
     const uint32_t sm_u32 = smem_u32(sm);
-    float *part = reinterpret_cast<float *>(sm + S::off_part);
-    float *csr_acc = reinterpret_cast<float *>(sm + S::off_csr);
-    int *srows = reinterpret_cast<int *>(sm + S::off_srows);
-    int *misc = reinterpret_cast<int *>(sm + S::off_misc);
-    float *hyb_tot = reinterpret_cast<float *>(sm + S::off_misc + 64);
-    float *xs = reinterpret_cast<float *>(sm + S::off_x);
-    const uint32_t xs_u32 = sm_u32 + S::off_x;
+    const int maxseg = p.maxseg;
+    float *part = reinterpret_cast<float *>(sm + C::off_part(maxseg));
+    float *csr_acc = reinterpret_cast<float *>(sm + C::off_csr(maxseg));
+    int *srows = reinterpret_cast<int *>(sm + C::off_srows(maxseg));
+    const uint32_t bar_u32 = sm_u32 + C::off_misc(maxseg);          // full[s] at +8s, empty[s] at +64+8s
+    int *misc = reinterpret_cast<int *>(sm + C::off_misc(maxseg) + 128);
+    float *hyb_tot = reinterpret_cast<float *>(sm + C::off_misc(maxseg) + 192);
+    float *xs = reinterpret_cast<float *>(sm + C::off_x(maxseg));
+    const uint32_t xs_u32 = sm_u32 + C::off_x(maxseg);
+    const uint32_t stage_u32 = sm_u32 + C::off_stage(maxseg);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = p.K, N = p.N, R = p.R;
+    const int N = p.N, R = p.R;
 
     // ---- this CTA's chunk of the flattened [strip][unit] space ----
     const int g0 = min((int)blockIdx.x * p.chunk, p.T);
@@ -285,51 +579,115 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
     const int s0 = g0 / R;
     const int r0 = g0 - s0 * R;
     const int nseg = len > 0 ? (g1 - 1) / R - s0 + 1 : 0;
+    const int nst = (len + SU - 1) / SU;  // pipeline stages this CTA will consume
 
-    // ---- stage LUTs (transposed to [value][slot]) and x ----
-    {
-        constexpr int L = 1 << BITS;
-        const int nel = nseg * STRIP * L;
-        for (int e = tid; e < nel; e += THREADS) {
-            const int v = e & (L - 1);
-            const int c = (e >> BITS) & (STRIP - 1);
-            const int seg = e >> (BITS + 6);
-            const int col = (s0 + seg) * STRIP + c;
-            const int slot = ((c & 3) << 4) | (c >> 2);
-            const uint32_t dst = sm_u32 + S::off_tab + seg * S::TAB + v * (STRIP * 4) + slot * 4;
-            if (col < N) cp_async4(dst, p.lut + (size_t)col * L + v);
-            else *reinterpret_cast<float *>(sm + S::off_tab + seg * S::TAB + v * (STRIP * 4) + slot * 4) = 0.f;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < C::NSTAGE; ++s) {
+            mbar_init(bar_u32 + 8 * s, 1);         // full: the producer's arrive.expect_tx
+            mbar_init(bar_u32 + 64 + 8 * s, NW);   // empty: one arrive per consumer warp
         }
-        if (p.x_is_half) {
-            const uint4 *xh = reinterpret_cast<const uint4 *>(p.x);
-            for (int e = tid; e < K / 8; e += THREADS) {
-                const uint4 u = __ldg(xh + e);
-                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
-                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-                const float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-                reinterpret_cast<float4 *>(xs)[2 * e] = make_float4(f0.x, f0.y, f1.x, f1.y);
-                reinterpret_cast<float4 *>(xs)[2 * e + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_launch_dependents();  // the next kernel in the stream may start its own (independent) prologue now
+    __syncthreads();
+
+    if (warp == WARP_PRODUCER) {
+        // =========================== TMA producer ===========================
+        // Weights never depend on the previous kernel, so this runs ahead of pdl_wait().
+        const uint64_t pol = l2_evict_first_policy();
+        constexpr int COPIES = SU * C::ROWS_PER_UNIT;  // 16 (w4) / 48 (w3) row copies per stage
+        for (int n = 0; n < nst; ++n) {
+            const int s = n % C::NSTAGE;
+            const uint32_t full = bar_u32 + 8 * s, empty = bar_u32 + 64 + 8 * s;
+            if (n >= C::NSTAGE) mbar_wait(empty, ((n / C::NSTAGE) - 1) & 1);
+            // each lane describes up to 2 copies: copy id -> (unit, row-in-unit)
+            uint32_t bytes[2] = {0u, 0u}, dst[2] = {0u, 0u};
+            const uint32_t *src[2] = {nullptr, nullptr};
+            uint32_t tot = 0;
+#pragma unroll
+            for (int h = 0; h < (COPIES + 31) / 32; ++h) {
+                const int cid = lane + 32 * h;
+                if (cid < COPIES) {
+                    const int u = cid / C::ROWS_PER_UNIT, rowin = cid - u * C::ROWS_PER_UNIT;
+                    const int o = n * SU + u;
+                    if (o < len) {
+                        UnitIt it;
+                        it.init(o, r0, R);
+                        const int c0 = (s0 + it.seg) * STRIP;
+                        bytes[h] = (uint32_t)min(STRIP, N - c0) * 4u;
+                        src[h] = p.qw + (size_t)(it.rr * C::ROWS_PER_UNIT + rowin) * N + c0;
+                        dst[h] = stage_u32 + s * C::STAGE_BYTES + cid * (STRIP * 4);
+                    }
+                }
+                tot += bytes[h];
             }
-        } else {
-            const float *xf = reinterpret_cast<const float *>(p.x);
-            for (int e = tid; e < K / 4; e += THREADS) cp_async16(xs_u32 + 16 * e, xf + 4 * e);
+            tot = __reduce_add_sync(0xffffffffu, tot);
+            if (lane == 0) mbar_expect_tx(full, tot);
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < (COPIES + 31) / 32; ++h)
+                if (bytes[h]) tma_bulk_g2s(dst[h], src[h], bytes[h], full, pol);
+        }
+    } else if (warp == WARP_SPARSE) {
+        sparse_warp<BITS, FUSED>(p, sm, sm_u32, lane, nseg, s0, r0, csr_acc, srows, hyb_tot);
+    } else {
+        // ---- consumers: stage the LUTs of this CTA's strips, transposed to [value][slot]; 2-way conflicts at worst ----
+        {
+            const int c = tid & (STRIP - 1), vg = tid >> 6;
+            const int slot = ((c & 3) << 4) | (c >> 2);
+            for (int seg = 0; seg < nseg; ++seg) {
+                const int col = (s0 + seg) * STRIP + c;
+                const uint32_t dst = sm_u32 + seg * C::TAB + slot * 4;
+#pragma unroll
+                for (int v = vg; v < C::L; v += 4) {
+                    if (col < N) cp_async4(dst + v * (STRIP * 4), p.lut + (size_t)col * C::L + v);
+                    else *reinterpret_cast<float *>(sm + seg * C::TAB + v * (STRIP * 4) + slot * 4) = 0.f;
+                }
+            }
+        }
+        for (int e = tid; e < MAXSEG * NW * STRIP; e += NW * 32) part[e] = 0.f;
+
+        pdl_wait();  // everything below reads data the previous kernel may have produced (x, mul, workspace)
+
+        // ---- stage the slice(s) of x this CTA needs, as fp32 ----
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int ua = seg == 0 ? r0 : 0;                               // first unit of the segment inside its strip
+            const int ub = min(R, r0 + len - seg * R);                      // one past the last
+            const int dst_unit = p.x_direct ? ua : (seg * R + ua - r0);     // compact: indexed by unit offset
+            const int nfl = (ub - ua) * C::XU;
+            const int src_f = ua * C::XU, dst_f = dst_unit * C::XU;
+            if (p.x_is_half) {
+                const __half *xh = reinterpret_cast<const __half *>(p.x) + src_f;
+                for (int e = tid; e < nfl / 8; e += NW * 32) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(xh) + e);
+                    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+                    const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+                    const float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+                    reinterpret_cast<float4 *>(xs + dst_f)[2 * e] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                    reinterpret_cast<float4 *>(xs + dst_f)[2 * e + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+                }
+            } else {
+                const float *xf = reinterpret_cast<const float *>(p.x) + src_f;
+                for (int e = tid; e < nfl / 4; e += NW * 32) cp_async16(xs_u32 + 4 * dst_f + 16 * e, xf + 4 * e);
+            }
         }
         cp_async_commit();
-        for (int e = tid; e < MAXSEG * NW * STRIP; e += THREADS) part[e] = 0.f;
-        for (int e = tid; e < MAXSEG * STRIP; e += THREADS) csr_acc[e] = 0.f;
+        cp_async_wait_all();
+        named_bar_sync(5, NW * 32);  // consumers only: LUTs, x slice, zeroed partials visible
     }
 
     const int i16 = lane & 15, jsel = lane >> 4;
 
     if (warp < NW) {
-        // =========================== dense warps ===========================
+        // =========================== consumer warps ===========================
         uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
         uint32_t ls[4] = {0u, 0u, 0u, 0u};
         uint32_t segc = 0u;
         int cur_seg = -1;
 
         auto set_seg = [&](int seg) {
-            const uint32_t tb = sm_u32 + S::off_tab + seg * S::TAB;
+            const uint32_t tb = sm_u32 + seg * C::TAB;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const uint32_t slot4 = ((((t ^ jsel) << 4) | i16) << 2);
@@ -354,229 +712,38 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
             for (int t = 0; t < 4; ++t) acc[t] = 0ull;
         };
 
-        UnitIt ld, cs;
-        ld.init(warp, r0, R);
-        cs.init(warp, r0, R);
-
-        if (BITS == 4) {
-            uint4 buf[PF4];
-            auto load4 = [&](const UnitIt &it) -> uint4 {
-                const int col0 = (s0 + it.seg) * STRIP + 4 * i16;
-                if (it.o < len && col0 < N) return ldg_stream(p.qw + (size_t)(it.rr + jsel) * N + col0);
-                return make_uint4(0u, 0u, 0u, 0u);
-            };
-#pragma unroll
-            for (int u = 0; u < PF4; ++u) { buf[u] = load4(ld); ld.next(R); }
-            cp_async_wait_all();
-            __syncthreads();  // LUTs, x, zeroed partials visible
-            while (cs.o < len) {
-#pragma unroll
-                for (int u = 0; u < PF4; ++u) {
-                    if (cs.o < len) {
-                        if (cs.seg != cur_seg) {
-                            if (cur_seg >= 0) deposit(cur_seg);
-                            cur_seg = cs.seg;
-                            set_seg(cur_seg);
-                        }
-                        consume4(buf[u], jsel, ls, segc, xs_u32 + 32 * (cs.rr + jsel), acc);
-                        buf[u] = load4(ld);
-                        ld.next(R);
-                        cs.next(R);
-                    }
-                }
+        // this lane's unit inside a stage: 2*warp + jsel ; its 16 bytes at column group i16
+        const uint32_t lane_off = (2 * warp + jsel) * C::UNIT_BYTES + i16 * 16;
+        UnitIt it;
+        it.init(2 * warp, r0, R);
+        Words<BITS> cur = {}, nxt = {};
+        if (nst > 0) {
+            mbar_wait(bar_u32, 0);
+            load_words(cur, stage_u32 + lane_off);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_u32 + 64);
+        }
+        for (int n = 0; n < nst; ++n) {
+            if (n + 1 < nst) {  // pull the next stage into registers before computing on this one
+                const int s = (n + 1) % C::NSTAGE;
+                mbar_wait(bar_u32 + 8 * s, ((n + 1) / C::NSTAGE) & 1);
+                load_words(nxt, stage_u32 + s * C::STAGE_BYTES + lane_off);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_u32 + 64 + 8 * s);
             }
-        } else {
-            Grp3 buf[PF3];
-            auto load3 = [&](const UnitIt &it) -> Grp3 {
-                Grp3 g;
-                const int col0 = (s0 + it.seg) * STRIP + 4 * i16;
-                if (it.o < len && col0 < N) {
-                    const uint32_t *q = p.qw + (size_t)(3 * (it.rr + jsel)) * N + col0;
-                    g.a = ldg_stream(q);
-                    g.b = ldg_stream(q + N);
-                    g.c = ldg_stream(q + 2 * (size_t)N);
-                } else {
-                    g.a = g.b = g.c = make_uint4(0u, 0u, 0u, 0u);
+            if (it.o < len) {  // warp-uniform: len and o are even, a pair never straddles the end
+                if (it.seg != cur_seg) {
+                    if (cur_seg >= 0) deposit(cur_seg);
+                    cur_seg = it.seg;
+                    set_seg(cur_seg);
                 }
-                return g;
-            };
-#pragma unroll
-            for (int u = 0; u < PF3; ++u) { buf[u] = load3(ld); ld.next(R); }
-            cp_async_wait_all();
-            __syncthreads();
-            while (cs.o < len) {
-#pragma unroll
-                for (int u = 0; u < PF3; ++u) {
-                    if (cs.o < len) {
-                        if (cs.seg != cur_seg) {
-                            if (cur_seg >= 0) deposit(cur_seg);
-                            cur_seg = cs.seg;
-                            set_seg(cur_seg);
-                        }
-                        consume3(buf[u], jsel, ls, xs_u32 + 128 * (cs.rr + jsel), acc);
-                        buf[u] = load3(ld);
-                        ld.next(R);
-                        cs.next(R);
-                    }
-                }
+                const int xunit = (p.x_direct ? it.rr : it.o) + jsel;
+                consume(cur, jsel, ls, segc, xs_u32 + (C::XU * 4) * xunit, acc);
             }
+            it.advance(SU, R);
+            cur = nxt;
         }
         if (cur_seg >= 0) deposit(cur_seg);
-    } else {
-        // =========================== sparse warp ===========================
-        // (1) row pointers of the strips whose first unit lives in this CTA
-        if (p.rows) {
-            for (int seg = 0; seg < nseg; ++seg) {
-                const bool owner = (seg > 0) || (r0 == 0);
-                if (!owner) continue;
-                const int c0 = (s0 + seg) * STRIP;
-                const int nc = min(STRIP, N - c0);
-                for (int t = lane; t <= nc; t += 32) srows[seg * SROWS_LD + t] = __ldg(p.rows + c0 + t);
-            }
-        }
-        cp_async_wait_all();
-        __syncthreads();  // matches the dense warps' barrier: x is in shared memory now
-
-        // (2) CSR outliers: deterministic per-row sums into csr_acc
-        if (p.rows) {
-            int *scols = reinterpret_cast<int *>(sm + S::off_stage(K));
-            float *svals = reinterpret_cast<float *>(sm + S::off_stage(K) + CSR_CH * 4);
-            const uint32_t scols_u32 = sm_u32 + S::off_stage(K), svals_u32 = scols_u32 + CSR_CH * 4;
-            for (int seg = 0; seg < nseg; ++seg) {
-                const bool owner = (seg > 0) || (r0 == 0);
-                if (!owner) continue;
-                const int c0 = (s0 + seg) * STRIP;
-                const int nc = min(STRIP, N - c0);
-                const int *sr = srows + seg * SROWS_LD;
-                float *out = csr_acc + seg * STRIP;
-                int cb = 0;
-                while (cb < nc) {
-                    const int base = sr[cb];
-                    int ce = cb + 1;
-                    while (ce < nc && sr[ce + 1] - base <= CSR_CH) ++ce;
-                    const int cnt = sr[ce] - base;
-                    if (cnt > CSR_CH) {  // one very long row: straight from global memory
-                        float a = 0.f;
-                        for (int e = base + lane; e < sr[cb + 1]; e += 32) a += __ldg(p.vals + e) * xs[__ldg(p.cols + e)];
-                        a = warp_sum(a);
-                        if (lane == 0) out[cb] = a;
-                        cb += 1;
-                        continue;
-                    }
-                    for (int e = lane; e < cnt; e += 32) {
-                        cp_async4(scols_u32 + 4 * e, p.cols + base + e);
-                        cp_async4(svals_u32 + 4 * e, p.vals + base + e);
-                    }
-                    cp_async_commit();
-                    cp_async_wait_all();
-                    __syncwarp();
-                    // pass 1: one lane per short row (sequential sum in storage order)
-                    for (int c = cb + lane; c < ce; c += 32) {
-                        const int a0 = sr[c] - base, a1 = sr[c + 1] - base;
-                        if (a1 - a0 <= 64) {
-                            float a = 0.f;
-                            for (int e = a0; e < a1; ++e) a += svals[e] * xs[scols[e]];
-                            out[c] = a;
-                        }
-                    }
-                    // pass 2: the whole warp on each long row
-                    for (int c = cb; c < ce; ++c) {
-                        const int a0 = sr[c] - base, a1 = sr[c + 1] - base;
-                        if (a1 - a0 > 64) {
-                            float a = 0.f;
-                            for (int e = a0 + lane; e < a1; e += 32) a += svals[e] * xs[scols[e]];
-                            a = warp_sum(a);
-                            if (lane == 0) out[c] = a;
-                        }
-                    }
-                    __syncwarp();
-                    cb = ce;
-                }
-            }
-        }
-
-        // (3) topX dense rows: CTA b < hc takes k-rows [b*hrows, (b+1)*hrows)
-        if (p.full_rows && (int)blockIdx.x < p.hc) {
-            const int kb = blockIdx.x * p.hrows, ke = min(K, kb + p.hrows);
-            for (int jb = 0; jb < p.topX; jb += 32) {
-                const int j = jb + lane;
-                float a = 0.f;
-                if (j < p.topX) {
-                    const float *fr = p.full_rows + (size_t)kb * p.topX + j;
-#pragma unroll 8
-                    for (int k = kb; k < ke; ++k, fr += p.topX) a += __ldg(fr) * xs[k];
-                    if (FUSED) {
-                        p.ws_hyb[(size_t)blockIdx.x * p.topX + j] = a;
-                        __threadfence();
-                    } else {
-                        const int c = __ldg(p.fri + j);
-                        if (c >= 0 && c < N) atomicAdd(reinterpret_cast<float *>(p.out) + c, a);
-                    }
-                }
-            }
-            if (FUSED) {
-                __syncwarp();
-                int last = 0;
-                if (lane == 0) {
-                    __threadfence();
-                    last = (atomicAdd(p.ws_hyb_cnt, 1) == p.hc - 1);
-                }
-                last = __shfl_sync(0xffffffffu, last, 0);
-                if (last) {
-                    __threadfence();
-                    if (lane == 0) *p.ws_hyb_cnt = 0;
-                    for (int j = 0; j < p.topX; ++j) {  // lanes stride over contributors, fixed xor tree -> deterministic
-                        float t = 0.f;
-#pragma unroll 4
-                        for (int b = lane; b < p.hc; b += 32) t += ldcg_f32(p.ws_hyb + (size_t)b * p.topX + j);
-                        t = warp_sum(t);
-                        if (lane == 0) hyb_tot[j] = t;
-                    }
-                    __syncwarp();
-                    // hand one "hybrid slot" vector to every strip that owns a dense-row output channel
-                    for (int j0 = 0; j0 < p.topX; ++j0) {
-                        const int cj0 = __ldg(p.fri + j0);
-                        if (cj0 < 0 || cj0 >= N) continue;
-                        const int strip = cj0 / STRIP;
-                        bool seen = false;
-                        for (int j = 0; j < j0; ++j) {
-                            const int cj = __ldg(p.fri + j);
-                            seen |= (cj >= 0 && cj < N && cj / STRIP == strip);
-                        }
-                        if (seen) continue;
-                        float v0 = 0.f, v1 = 0.f;  // columns lane, lane+32 of the strip
-                        for (int j = j0; j < p.topX; ++j) {
-                            const int cj = __ldg(p.fri + j);
-                            if (cj >= 0 && cj < N && cj / STRIP == strip) {
-                                const int cc = cj - strip * STRIP;
-                                if (cc == lane) v0 += hyb_tot[j];
-                                if (cc == lane + 32) v1 += hyb_tot[j];
-                            }
-                        }
-                        float *slot = p.ws_part + ((size_t)strip * (p.maxc + 1) + p.maxc) * STRIP;
-                        slot[lane] = v0;
-                        slot[lane + 32] = v1;
-                        __threadfence();
-                        __syncwarp();
-                        const int first = (int)(((long long)strip * R) / p.chunk);
-                        const int lastc = (int)((((long long)strip + 1) * R - 1) / p.chunk);
-                        const int nd = lastc - first + 1;
-                        int fin = 0;
-                        if (lane == 0) {
-                            __threadfence();
-                            fin = (atomicAdd(p.ws_cnt + strip, 1) == nd);  // nd dense contributors + this one
-                            if (fin) p.ws_cnt[strip] = 0;
-                        }
-                        fin = __shfl_sync(0xffffffffu, fin, 0);
-                        if (fin) {
-                            __threadfence();
-                            final_store(p, strip, lane, nd, true);
-                            final_store(p, strip, lane + 32, nd, true);
-                        }
-                    }
-                }
-            }
-        }
     }
 
     __syncthreads();  // all partials of this CTA are in shared memory
@@ -619,7 +786,7 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
         }
         // ticket: 64 threads (2 warps) per segment; sync them with a named barrier per segment
         const bool ticketed = active && !(nd == 1 && !hyb);
-        asm volatile("bar.sync %0, 64;" ::"r"(seg + 1));
+        named_bar_sync(seg + 1, 64);
         if (c == 0) {
             int fin = 0;
             if (ticketed) {
@@ -629,7 +796,7 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
             }
             misc[seg] = fin;
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(seg + 1));
+        named_bar_sync(seg + 1, 64);
         if (misc[seg]) {
             __threadfence();
             final_store(p, strip, c, nd, hyb);
@@ -677,8 +844,14 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
-struct DevInfo { int sm = 0; int occ[2][2] = {{0, 0}, {0, 0}}; int occ_smem[2][2] = {{-1, -1}, {-1, -1}}; bool attr_set = false; };
+struct DevInfo {
+    int sm = 0;
+    bool attr_set = false;
+    int occ_key[2][2] = {{-1, -1}, {-1, -1}};
+    int occ_val[2][2] = {{0, 0}, {0, 0}};
+};
 DevInfo g_dev[64];
+int g_use_pdl = -1;
 
 template <int BITS, bool FUSED>
 int occupancy(int smem) {
@@ -687,10 +860,23 @@ int occupancy(int smem) {
     return occ;
 }
 
+int query_occ(DevInfo &d, int bits, bool fused, int smem) {
+    const int bi = bits == 4 ? 1 : 0, fi = fused ? 1 : 0;
+    if (d.occ_key[bi][fi] != smem) {
+        d.occ_val[bi][fi] = bits == 4 ? (fused ? occupancy<4, true>(smem) : occupancy<4, false>(smem))
+                                      : (fused ? occupancy<3, true>(smem) : occupancy<3, false>(smem));
+        d.occ_key[bi][fi] = smem;
+    }
+    return d.occ_val[bi][fi];
+}
+
 struct Plan {
-    int R, strips, T, chunk, G, maxc, hc, hrows, smem;
+    int R, strips, T, chunk, G, maxc, hc, hrows, smem, maxseg, x_direct, xfloats;
     size_t ws_cnt_off, ws_hybcnt_off, ws_hyb_off, ws_part_off, ws_bytes;
 };
+
+template <int BITS>
+int smem_for(int maxseg, int xfloats, bool csr) { return Cfg<BITS>::total(maxseg, xfloats, csr); }
 
 int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &pl) {
     int dev = 0;
@@ -710,39 +896,50 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &
         if (cudaGetLastError() != cudaSuccess) return fail(SQLLM_ECUDA, "cudaFuncSetAttribute failed");
         d.attr_set = true;
     }
-    pl.smem = bits == 4 ? Smem<4>::total(K, has_csr) : Smem<3>::total(K, has_csr);
-    if (pl.smem > 227 * 1024) return fail(SQLLM_EINVAL, "in_features=%d needs %d B of shared memory (> 227 KB)", K, pl.smem);
-    const int bi = bits == 4 ? 1 : 0, fi = fused ? 1 : 0;
-    if (d.occ_smem[bi][fi] != pl.smem) {
-        int o = bits == 4 ? (fused ? occupancy<4, true>(pl.smem) : occupancy<4, false>(pl.smem))
-                          : (fused ? occupancy<3, true>(pl.smem) : occupancy<3, false>(pl.smem));
-        if (o <= 0) return fail(SQLLM_ECUDA, "kernel cannot be resident (smem %d B)", pl.smem);
-        d.occ[bi][fi] = o;
-        d.occ_smem[bi][fi] = pl.smem;
-    }
+    const int XU = bits == 4 ? 8 : 32;
     pl.R = bits == 4 ? K / 8 : K / 32;
     pl.strips = (N + STRIP - 1) / STRIP;
     const long long T = (long long)pl.strips * pl.R;
     if (T > 0x3fffffff) return fail(SQLLM_EINVAL, "problem too large");
     pl.T = (int)T;
-    int G = d.sm * d.occ[bi][fi];
-    int chunk = (int)(2 * ((T + 2LL * G - 1) / (2LL * G)));
-    if (chunk > 3 * pl.R) chunk = 3 * pl.R;  // a CTA may touch at most MAXSEG strips
-    if (chunk < 2) chunk = 2;
+    if (pl.strips > MAX_STRIPS) return fail(SQLLM_EINVAL, "out_features=%d exceeds the %d-strip workspace header", N, MAX_STRIPS);
+
+    // The grid depends on occupancy, occupancy on shared memory, shared memory on the chunk (x slice): iterate to a
+    // fixed point starting from the leanest guess (2 strips per CTA, compact x).
+    int occ = 1, chunk = 2, maxseg = 2, xfl = 0, smem = 0;
+    for (int iter = 0; iter < 4; ++iter) {
+        const int G0 = d.sm * occ;
+        chunk = (int)(2 * ((T + 2LL * G0 - 1) / (2LL * G0)));
+        if (chunk > 3 * pl.R) chunk = 3 * pl.R;  // a CTA may touch at most MAXSEG strips
+        if (chunk < 2) chunk = 2;
+        maxseg = (chunk - 2) / pl.R + 2;          // worst case over start offsets (even offsets, even R)
+        if (maxseg > MAXSEG) maxseg = MAXSEG;
+        const bool direct = (long long)chunk * XU >= K;
+        xfl = direct ? K : chunk * XU;
+        pl.x_direct = direct ? 1 : 0;
+        smem = bits == 4 ? smem_for<4>(maxseg, xfl, has_csr) : smem_for<3>(maxseg, xfl, has_csr);
+        if (smem > 227 * 1024) return fail(SQLLM_EINVAL, "in_features=%d needs %d B of shared memory (> 227 KB)", K, smem);
+        const int o = query_occ(d, bits, fused, smem);
+        if (o <= 0) return fail(SQLLM_ECUDA, "kernel cannot be resident (smem %d B)", smem);
+        if (o == occ && iter > 0) break;
+        occ = o;
+    }
+    pl.smem = smem;
+    pl.maxseg = maxseg;
+    pl.xfloats = xfl;
     pl.chunk = chunk;
     pl.G = (int)((T + chunk - 1) / chunk);
     pl.maxc = (pl.R - 1) / chunk + 2;
     pl.hc = 0;
     pl.hrows = 0;
     if (topX > 0) {
-        int hc = pl.G < K / 16 ? pl.G : K / 16;
+        int hc = pl.G < K / 8 ? pl.G : K / 8;
         if (hc < 1) hc = 1;
         pl.hrows = (K + hc - 1) / hc;
         pl.hc = (K + pl.hrows - 1) / pl.hrows;
     }
     // Fixed header: [0,4) dense-row ticket, [256, 256+4*MAX_STRIPS) per-strip tickets.  Tickets must never
     // share bytes with data regions of ANY shape (the workspace is reused across layers of different sizes).
-    if (pl.strips > MAX_STRIPS) return fail(SQLLM_EINVAL, "out_features=%d exceeds the %d-strip workspace header", N, MAX_STRIPS);
     size_t off = WS_HEADER;
     pl.ws_hybcnt_off = 0;
     pl.ws_cnt_off = 256;
@@ -765,6 +962,26 @@ int check_common(const sqllm_lutgemv_args *a) {
     return SQLLM_OK;
 }
 
+template <int BITS, bool FUSED>
+cudaError_t launch_kernel(const Plan &pl, const Params &p, cudaStream_t st) {
+    if (g_use_pdl < 0) {
+        const char *e = getenv("SQLLM_NO_PDL");
+        g_use_pdl = (e && e[0] == '1') ? 0 : 1;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(pl.G);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, lutgemv_kernel<BITS, FUSED>, p);
+}
+
 template <bool FUSED>
 int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t st) {
     p.qw = reinterpret_cast<const uint32_t *>(a->qweight);
@@ -776,11 +993,10 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
     p.topX = hyb ? a->topX : 0;
     p.K = a->in_features; p.N = a->out_features;
     p.R = pl.R; p.strips = pl.strips; p.T = pl.T; p.chunk = pl.chunk;
+    p.maxseg = pl.maxseg; p.x_direct = pl.x_direct; p.xfloats = pl.xfloats;
     p.hc = hyb ? pl.hc : 0; p.hrows = pl.hrows; p.maxc = pl.maxc;
-    p.has_csr_stage = a->rows ? 1 : 0;
-    if (a->bits == 4) lutgemv_kernel<4, FUSED><<<pl.G, THREADS, pl.smem, st>>>(p);
-    else lutgemv_kernel<3, FUSED><<<pl.G, THREADS, pl.smem, st>>>(p);
-    const cudaError_t e = cudaGetLastError();
+    p.has_csr = a->rows ? 1 : 0;
+    const cudaError_t e = a->bits == 4 ? launch_kernel<4, FUSED>(pl, p, st) : launch_kernel<3, FUSED>(pl, p, st);
     if (e != cudaSuccess) return fail(SQLLM_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return SQLLM_OK;
 }
@@ -806,8 +1022,7 @@ size_t sqllm_workspace_bytes(int bits, int in_features, int out_features, int to
     Plan pl;
     if (bits != 3 && bits != 4) return 0;
     if (in_features <= 0 || in_features % 64 || out_features <= 0) return 0;
-    // worst case over csr staging on/off: the larger shared-memory footprint gives the smaller grid,
-    // hence the larger chunk; take the max of both plans.
+    // CSR staging changes the shared-memory footprint, hence occupancy, grid and chunk: take the max of both plans.
     size_t b = 0;
     for (int csr = 0; csr < 2; ++csr)
         if (make_plan(bits, in_features, out_features, topX, csr != 0, true, pl) == SQLLM_OK && pl.ws_bytes > b) b = pl.ws_bytes;

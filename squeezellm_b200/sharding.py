@@ -1,0 +1,86 @@
+"""Column sharding of a QuantLinearLUT across GPUs (BASELINE.json north_star).
+
+The reference has no multi-GPU code at all.  Output channels are independent: column c of `qweight`, row c of
+`lookup_table`, CSR row c and the dense-row entries whose `full_row_indices` equal c are all that y[c] needs (plus the
+whole x).  Rank r of P therefore owns a contiguous range of output channels [c0, c1):
+
+    qweight[:, c0:c1]   lookup_table[c0:c1]   rows[c0:c1+1] - rows[c0], cols/vals[rows[c0]:rows[c1]]
+    full_rows[:, j], full_row_indices[j] - c0   for the j with c0 <= full_row_indices[j] < c1     (others dropped)
+
+and computes its slice of y with the ordinary single-GPU kernel; the full output vector is the sum of the
+zero-padded slices - ONE all-reduce (sum) on the output vector, as north_star specifies.  Ranges are cut on multiples
+of 4 channels (the kernel's only width requirement; the reference kernel would need multiples of 128, which 22016/8
+cannot give - SURVEY.md 8(e)).
+
+`shard_bounds`, `shard_state` are pure functions on CPU tensors (testable with gloo); `ShardedQuantLinearLUT` is the
+module that runs the local shard on its GPU and all-reduces.  `matvec_fn` lets tests substitute the CPU oracle for the
+local compute - the product path always uses the CUDA module.
+"""
+import torch
+import torch.nn as nn
+
+
+def shard_bounds(outfeatures, world, align=4):
+    """Contiguous, `align`-aligned, as-equal-as-possible output ranges: list of (c0, c1), len == world."""
+    assert outfeatures % align == 0, f"outfeatures={outfeatures} must be a multiple of {align}"
+    units = outfeatures // align
+    base, extra = divmod(units, world)
+    bounds, c = [], 0
+    for r in range(world):
+        n = (base + (1 if r < extra else 0)) * align
+        bounds.append((c, c + n))
+        c += n
+    assert c == outfeatures
+    return bounds
+
+
+def shard_state(state, c0, c1):
+    """Slice a QuantLinearLUT state dict (reference buffer names, squeezellm/quant.py:48-95) to channels [c0, c1)."""
+    out = {"qweight": state["qweight"][:, c0:c1].contiguous(), "lookup_table": state["lookup_table"][c0:c1].contiguous()}
+    if state.get("bias") is not None:
+        out["bias"] = state["bias"][c0:c1].contiguous()
+    if state.get("rows") is not None:
+        rows = state["rows"]
+        a, b = int(rows[c0]), int(rows[c1])
+        out["rows"] = (rows[c0:c1 + 1] - rows[c0]).to(torch.int32).contiguous()
+        out["cols"] = state["cols"][a:b].contiguous()
+        out["vals"] = state["vals"][a:b].contiguous()
+    if state.get("full_rows") is not None:
+        idx = state["full_row_indices"]
+        keep = torch.nonzero((idx >= c0) & (idx < c1)).flatten()
+        # keep the dense-row count fixed across ranks (buffers of identical shape): dropped columns become zero columns
+        fr = torch.zeros_like(state["full_rows"])
+        fi = torch.zeros_like(idx)
+        fr[:, :len(keep)] = state["full_rows"][:, keep]
+        fi[:len(keep)] = (idx[keep] - c0).to(idx.dtype)
+        out["full_rows"], out["full_row_indices"] = fr.contiguous(), fi.contiguous()
+    return out
+
+
+class ShardedQuantLinearLUT(nn.Module):
+    """One rank's column shard of a QuantLinearLUT + the all-reduce that rebuilds the full output vector."""
+
+    def __init__(self, local, outfeatures, c0, c1, group=None, matvec_fn=None):
+        super().__init__()
+        self.local = local                  # QuantLinearLUT over channels [c0, c1)  (or None when matvec_fn is given)
+        self.outfeatures, self.c0, self.c1, self.group = outfeatures, c0, c1, group
+        self.matvec_fn = matvec_fn          # tests: CPU stand-in for the local compute
+
+    @classmethod
+    def from_full(cls, full_state, bits, infeatures, outfeatures, rank, world, include_sparse, topX, device, group=None):
+        from .quant import QuantLinearLUT
+        c0, c1 = shard_bounds(outfeatures, world)[rank]
+        st = shard_state(full_state, c0, c1)
+        m = QuantLinearLUT(bits, infeatures, c1 - c0, "bias" in st, include_sparse=include_sparse,
+                           numvals=int(st["vals"].numel()) if "vals" in st else 0, topX=topX)
+        m.load_state_dict(st, strict=False)
+        return cls(m.to(device), outfeatures, c0, c1, group)
+
+    def forward(self, x):
+        import torch.distributed as dist
+        y_local = self.matvec_fn(x) if self.matvec_fn is not None else self.local(x)
+        lead = y_local.shape[:-1]
+        full = torch.zeros(lead + (self.outfeatures,), dtype=y_local.dtype, device=y_local.device)
+        full[..., self.c0:self.c1] = y_local
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)  # sum of zero-padded slices
+        return full

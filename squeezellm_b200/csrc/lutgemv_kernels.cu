@@ -28,6 +28,7 @@
 //     red.add.f32 per (CTA, column).  Fused mode (QuantLinearLUT.forward fast path) writes partials
 //     to a workspace; the last-arriving CTA of each strip (atomic ticket, no spinning) sums them in
 //     fixed order, adds bias, converts and stores -> deterministic, no pre-zeroed output.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -36,11 +37,23 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "sqllm_b200.h"
 
 namespace {
 
-constexpr int NW = 8;                     // consumer warps per CTA
+#ifndef SQLLM_NW
+#define SQLLM_NW 8
+#endif
+#ifndef SQLLM_MINB4
+#define SQLLM_MINB4 4
+#endif
+#ifndef SQLLM_MINB3
+#define SQLLM_MINB3 3
+#endif
+constexpr int NW = SQLLM_NW;              // consumer warps per CTA (multiple of 8)
 constexpr int WARP_PRODUCER = NW;         // warp index of the TMA producer
 constexpr int WARP_SPARSE = NW + 1;       // warp index of the CSR / dense-row warp
 constexpr int THREADS = (NW + 2) * 32;
@@ -52,6 +65,7 @@ constexpr int SROWS_LD = 68;              // padded row-pointer slice per segmen
 constexpr int MAX_TOPX_FUSED = 128;
 constexpr int MAX_STRIPS = 16320;         // per-strip tickets in the workspace header (out_features <= 1,044,480)
 constexpr size_t WS_HEADER = 65536;
+constexpr int MAX_NSTAGE = 16;            // weight stages per CTA (runtime count, fills the shared-memory budget)
 
 struct Params {
     const uint32_t *qw;
@@ -70,6 +84,8 @@ struct Params {
     int T;        // strips * R
     int chunk;    // units per CTA (even)
     int maxseg;   // strips a CTA of this launch can touch (sizes the LUT tables)
+    int nstage;   // weight stages in the TMA ring
+    int tma2d;    // 1: stages are fetched with 2-D tensor-map TMA boxes, 0: row-by-row bulk copies (odd shapes)
     int x_direct; // 1: x staged at its natural index (CTA covers whole strips), 0: compact, indexed by unit offset
     int xfloats;  // floats in the x staging buffer
     int hc;       // CTAs that take a slice of the dense rows
@@ -81,6 +97,8 @@ struct Params {
     float *ws_hyb;    // [hc][topX]
     int *ws_hyb_cnt;  // [1]
     int has_csr;
+    int dbg;                    // debug: 1 = skip the gather/FMA math, 2 = no work at all, 4 = skip LUT staging (SQLLM_DEBUG_FLAGS)
+    unsigned long long *trace;  // debug timeline (only written when built with -DSQLLM_TRACE and non-null)
 };
 
 // ---- per-bit-width constants and the shared memory carve-up (offsets from a 4 KB aligned base) ---
@@ -92,18 +110,24 @@ struct Cfg {
     static constexpr int XU = BITS == 4 ? 8 : 32;          // inputs per unit
     static constexpr int UNIT_BYTES = ROWS_PER_UNIT * STRIP * 4;
     static constexpr int STAGE_BYTES = SU * UNIT_BYTES;    // 4 KB (w4) / 12 KB (w3)
-    static constexpr int NSTAGE = BITS == 4 ? 6 : 3;
-    // layout: [tables maxseg*TAB][stages][part][csr_acc][srows][misc][x][csr stage]
-    __host__ __device__ static int off_stage(int maxseg) { return maxseg * TAB; }
-    __host__ __device__ static int off_part(int maxseg) { return off_stage(maxseg) + NSTAGE * STAGE_BYTES; }
-    __host__ __device__ static int off_csr(int maxseg) { return off_part(maxseg) + MAXSEG * NW * STRIP * 4; }
+    // 2-D TMA box: BU units tall (w4: a whole stage of 16 rows; w3: 4 groups = 12 rows), 64 columns wide.
+    // in_features % 128 == 0 (the reference's own precondition) makes every box lie inside one strip.
+    static constexpr int BU = BITS == 4 ? SU : 4;
+    static constexpr int BOX_ROWS = BU * ROWS_PER_UNIT;
+    static constexpr int BOX_BYTES = BOX_ROWS * STRIP * 4;
+    // layout: [tables maxseg*TAB][part maxseg][csr_acc][srows][misc][x][csr stage][weight stages ...]
+    __host__ __device__ static int off_part(int maxseg) { return maxseg * TAB; }
+    __host__ __device__ static int off_csr(int maxseg) { return off_part(maxseg) + maxseg * NW * STRIP * 4; }
     __host__ __device__ static int off_srows(int maxseg) { return off_csr(maxseg) + MAXSEG * STRIP * 4; }
     __host__ __device__ static int off_misc(int maxseg) { return off_srows(maxseg) + MAXSEG * SROWS_LD * 4; }
-    // misc: 16 mbarriers (128 B) + 16 ints (64 B) + float[MAX_TOPX_FUSED]
-    __host__ __device__ static int off_x(int maxseg) { return off_misc(maxseg) + 128 + 64 + MAX_TOPX_FUSED * 4; }
+    // misc: 2 x MAX_NSTAGE mbarriers (256 B) + 16 ints (64 B) + float[MAX_TOPX_FUSED]
+    __host__ __device__ static int off_x(int maxseg) { return off_misc(maxseg) + 256 + 64 + MAX_TOPX_FUSED * 4; }
     __host__ __device__ static int off_cstage(int maxseg, int xfloats) { return off_x(maxseg) + ((xfloats * 4 + 15) & ~15); }
-    __host__ __device__ static int total(int maxseg, int xfloats, bool csr) {
-        return 4096 + off_cstage(maxseg, xfloats) + (csr ? CSR_CH * 8 : 0);
+    __host__ __device__ static int off_stage(int maxseg, int xfloats, bool csr) {
+        return (off_cstage(maxseg, xfloats) + (csr ? CSR_CH * 8 : 0) + 127) & ~127;
+    }
+    __host__ __device__ static int total(int maxseg, int xfloats, bool csr, int nstage) {
+        return 4096 + off_stage(maxseg, xfloats, csr) + nstage * STAGE_BYTES;
     }
 };
 
@@ -151,6 +175,18 @@ __device__ __forceinline__ float warp_sum(float v) {  // fixed xor tree -> deter
     return v;
 }
 __device__ __forceinline__ float ldcg_f32(const float *p) { return __ldcg(p); }
+#ifdef SQLLM_TRACE
+__device__ __forceinline__ void trace_mark(const Params &p, int slot) {
+    if (p.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[(size_t)blockIdx.x * 32 + slot] = t;
+    }
+}
+#define TRACE(slot, cond) do { if (cond) trace_mark(p, slot); } while (0)
+#else
+#define TRACE(slot, cond) do { } while (0)
+#endif
 
 // mbarrier / TMA bulk copy / PDL
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -165,8 +201,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
+#ifdef SQLLM_SPIN_WAIT
+        asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#else
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     } while (!ok);
 }
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
@@ -177,6 +218,10 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_tile2d_g2s(uint32_t dst, const CUtensorMap *map, int col, int row, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -205,7 +250,7 @@ struct UnitIt {
 //   E/O hold the even/odd nibbles of a word in separate bytes, already OR-ed with bits 12..15 of the
 //   table address; PRMT then builds the complete LDS address: {ls.b3, ls.b2, E.b_n, ls.b0}.
 // =================================================================================================
-__device__ __forceinline__ void consume4(const uint4 q, const int jsel, const uint32_t (&ls)[4], const uint32_t segc,
+__device__ __forceinline__ void consume4(const uint4 q, const int jsel, const uint32_t lsb, const uint32_t segc,
                                          const uint32_t xaddr, uint64_t (&acc)[4]) {
     const float4 xa = lds_v4(xaddr), xb = lds_v4(xaddr + 16);
     const uint64_t x01 = pack2(xa.x, xa.y), x23 = pack2(xa.z, xa.w), x45 = pack2(xb.x, xb.y), x67 = pack2(xb.z, xb.w);
@@ -215,10 +260,11 @@ __device__ __forceinline__ void consume4(const uint4 q, const int jsel, const ui
     for (int t = 0; t < 4; ++t) {
         const uint32_t E = (w[t] & 0x0F0F0F0Fu) | segc;
         const uint32_t O = ((w[t] >> 4) & 0x0F0F0F0Fu) | segc;
-        const float e0 = lds_f32(__byte_perm(E, ls[t], 0x7604)), o0 = lds_f32(__byte_perm(O, ls[t], 0x7604));
-        const float e1 = lds_f32(__byte_perm(E, ls[t], 0x7614)), o1 = lds_f32(__byte_perm(O, ls[t], 0x7614));
-        const float e2 = lds_f32(__byte_perm(E, ls[t], 0x7624)), o2 = lds_f32(__byte_perm(O, ls[t], 0x7624));
-        const float e3 = lds_f32(__byte_perm(E, ls[t], 0x7634)), o3 = lds_f32(__byte_perm(O, ls[t], 0x7634));
+        const uint32_t l = lsb ^ (uint32_t)(t << 6);  // slot of column t (the lane's bank), see set_seg
+        const float e0 = lds_f32(__byte_perm(E, l, 0x7604)), o0 = lds_f32(__byte_perm(O, l, 0x7604));
+        const float e1 = lds_f32(__byte_perm(E, l, 0x7614)), o1 = lds_f32(__byte_perm(O, l, 0x7614));
+        const float e2 = lds_f32(__byte_perm(E, l, 0x7624)), o2 = lds_f32(__byte_perm(O, l, 0x7624));
+        const float e3 = lds_f32(__byte_perm(E, l, 0x7634)), o3 = lds_f32(__byte_perm(O, l, 0x7634));
         ffma2(acc[t], pack2(e0, o0), x01);
         ffma2(acc[t], pack2(e1, o1), x23);
         ffma2(acc[t], pack2(e2, o2), x45);
@@ -269,11 +315,11 @@ template <int BITS> struct Words;
 template <> struct Words<4> { uint4 a; };
 template <> struct Words<3> { uint4 a, b, c; };
 
-__device__ __forceinline__ void consume(const Words<4> &g, const int jsel, const uint32_t (&ls)[4], const uint32_t segc,
+__device__ __forceinline__ void consume(const Words<4> &g, const int jsel, const uint32_t lsb, const uint32_t segc,
                                         const uint32_t xaddr, uint64_t (&acc)[4]) {
-    consume4(g.a, jsel, ls, segc, xaddr, acc);
+    consume4(g.a, jsel, lsb, segc, xaddr, acc);
 }
-__device__ __forceinline__ void consume(const Words<3> &g, const int jsel, const uint32_t (&ls)[4], const uint32_t,
+__device__ __forceinline__ void consume(const Words<3> &g, const int jsel, const uint32_t lsb, const uint32_t,
                                         const uint32_t xaddr, uint64_t (&acc)[4]) {
     uint64_t xp[16];
 #pragma unroll
@@ -286,7 +332,7 @@ __device__ __forceinline__ void consume(const Words<3> &g, const int jsel, const
     const uint32_t b[4] = {jsel ? g.b.y : g.b.x, jsel ? g.b.x : g.b.y, jsel ? g.b.w : g.b.z, jsel ? g.b.z : g.b.w};
     const uint32_t c[4] = {jsel ? g.c.y : g.c.x, jsel ? g.c.x : g.c.y, jsel ? g.c.w : g.c.z, jsel ? g.c.z : g.c.w};
 #pragma unroll
-    for (int t = 0; t < 4; ++t) consume3_col(a[t], b[t], c[t], ls[t], xp, acc[t]);
+    for (int t = 0; t < 4; ++t) consume3_col(a[t], b[t], c[t], lsb ^ (uint32_t)(t << 6), xp, acc[t]);
 }
 __device__ __forceinline__ void load_words(Words<4> &g, uint32_t unit_addr) { g.a = lds_u4(unit_addr); }
 __device__ __forceinline__ void load_words(Words<3> &g, uint32_t unit_addr) {
@@ -388,7 +434,12 @@ __device__ __forceinline__ void sparse_warp(const Params &p, unsigned char *sm, 
         }
     }
 
+#ifdef SQLLM_WAIT_ALL
     pdl_wait();
+#else
+    if (lane == 0) pdl_wait();
+    __syncwarp();
+#endif
 
     // ---------------- phase B: needs x (and, in fused mode, the workspace) ----------------
     // (1) topX dense rows: CTA b < hc takes k-rows [kb, ke)
@@ -553,102 +604,153 @@ __device__ __forceinline__ void sparse_warp(const Params &p, unsigned char *sm, 
 // The kernel
 // =================================================================================================
 template <int BITS, bool FUSED>
-__global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
+__global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3) lutgemv_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     using C = Cfg<BITS>;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 4095) & ~uintptr_t(4095));
-    const uint32_t sm_u32 = smem_u32(sm);
+    // 4 KB aligned base, computed in the 32-bit shared window and pinned in a register (an opaque mov: otherwise the
+    // compiler rematerialises it - S2UR + uniform adds - at every use once registers get tight)
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    uint32_t sm_u32 = (raw_u32 + 4095u) & ~4095u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(sm_u32));
+    unsigned char *sm = smem_raw + (sm_u32 - raw_u32);
     const int maxseg = p.maxseg;
     float *part = reinterpret_cast<float *>(sm + C::off_part(maxseg));
     float *csr_acc = reinterpret_cast<float *>(sm + C::off_csr(maxseg));
     int *srows = reinterpret_cast<int *>(sm + C::off_srows(maxseg));
-    const uint32_t bar_u32 = sm_u32 + C::off_misc(maxseg);          // full[s] at +8s, empty[s] at +64+8s
-    int *misc = reinterpret_cast<int *>(sm + C::off_misc(maxseg) + 128);
-    float *hyb_tot = reinterpret_cast<float *>(sm + C::off_misc(maxseg) + 192);
+    const uint32_t bar_u32 = sm_u32 + C::off_misc(maxseg);          // full[s] at +8s, empty[s] at +128+8s
+    int *misc = reinterpret_cast<int *>(sm + C::off_misc(maxseg) + 256);
+    float *hyb_tot = reinterpret_cast<float *>(sm + C::off_misc(maxseg) + 320);
     float *xs = reinterpret_cast<float *>(sm + C::off_x(maxseg));
     const uint32_t xs_u32 = sm_u32 + C::off_x(maxseg);
-    const uint32_t stage_u32 = sm_u32 + C::off_stage(maxseg);
+    const uint32_t stage_u32 = sm_u32 + C::off_stage(maxseg, p.xfloats, p.has_csr != 0);
+    const int nstage = p.nstage;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, R = p.R;
 
     // ---- this CTA's chunk of the flattened [strip][unit] space ----
     const int g0 = min((int)blockIdx.x * p.chunk, p.T);
-    const int g1 = min(g0 + p.chunk, p.T);
+    const int g1 = (p.dbg & 2) ? g0 : min(g0 + p.chunk, p.T);
     const int len = g1 - g0;
     const int s0 = g0 / R;
     const int r0 = g0 - s0 * R;
     const int nseg = len > 0 ? (g1 - 1) / R - s0 + 1 : 0;
     const int nst = (len + SU - 1) / SU;  // pipeline stages this CTA will consume
 
+    TRACE(0, tid == 0);
+#ifdef SQLLM_TRACE
+    if (p.trace && tid == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); p.trace[(size_t)blockIdx.x * 32 + 12] = smid + 1; }
+#endif
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < C::NSTAGE; ++s) {
-            mbar_init(bar_u32 + 8 * s, 1);         // full: the producer's arrive.expect_tx
-            mbar_init(bar_u32 + 64 + 8 * s, NW);   // empty: one arrive per consumer warp
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(bar_u32 + 8 * s, 1);          // full: the producer's arrive.expect_tx
+            mbar_init(bar_u32 + 128 + 8 * s, NW);   // empty: one arrive per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_launch_dependents();  // the next kernel in the stream may start its own (independent) prologue now
     __syncthreads();
+    TRACE(1, tid == 0);
 
     if (warp == WARP_PRODUCER) {
         // =========================== TMA producer ===========================
         // Weights never depend on the previous kernel, so this runs ahead of pdl_wait().
         const uint64_t pol = l2_evict_first_policy();
-        constexpr int COPIES = SU * C::ROWS_PER_UNIT;  // 16 (w4) / 48 (w3) row copies per stage
-        for (int n = 0; n < nst; ++n) {
-            const int s = n % C::NSTAGE;
-            const uint32_t full = bar_u32 + 8 * s, empty = bar_u32 + 64 + 8 * s;
-            if (n >= C::NSTAGE) mbar_wait(empty, ((n / C::NSTAGE) - 1) & 1);
-            // each lane describes up to 2 copies: copy id -> (unit, row-in-unit)
-            uint32_t bytes[2] = {0u, 0u}, dst[2] = {0u, 0u};
-            const uint32_t *src[2] = {nullptr, nullptr};
-            uint32_t tot = 0;
-#pragma unroll
-            for (int h = 0; h < (COPIES + 31) / 32; ++h) {
-                const int cid = lane + 32 * h;
-                if (cid < COPIES) {
-                    const int u = cid / C::ROWS_PER_UNIT, rowin = cid - u * C::ROWS_PER_UNIT;
-                    const int o = n * SU + u;
-                    if (o < len) {
-                        UnitIt it;
-                        it.init(o, r0, R);
-                        const int c0 = (s0 + it.seg) * STRIP;
-                        bytes[h] = (uint32_t)min(STRIP, N - c0) * 4u;
-                        src[h] = p.qw + (size_t)(it.rr * C::ROWS_PER_UNIT + rowin) * N + c0;
-                        dst[h] = stage_u32 + s * C::STAGE_BYTES + cid * (STRIP * 4);
+        if (p.tma2d) {
+            // One tensor-map box per BU units: hardware address generation.  The loop is a single latency-bound warp, so it
+            // carries no divisions or re-derivations: ring slot, phase and box coordinates are all advanced incrementally.
+            constexpr int BOXES = SU / C::BU;  // 1 (w4) / 4 (w3): lane b owns box b of every stage
+            if (lane < BOXES) {
+                constexpr uint32_t MASK = (1u << BOXES) - 1u;
+                UnitIt it;
+                it.init(lane * C::BU, r0, R);
+                uint32_t full = bar_u32, empty = bar_u32 + 128, dst = stage_u32 + lane * C::BOX_BYTES;
+                int s = 0;
+                uint32_t ph = 0;
+                bool refill = false;
+                for (int n = 0; n < nst; ++n) {
+                    if (refill) mbar_wait(empty, ph);
+                    if (lane == 0) mbar_expect_tx(full, (uint32_t)min(BOXES, (len - it.o + C::BU - 1) / C::BU) * C::BOX_BYTES);
+                    if (BOXES > 1) __syncwarp(MASK);
+                    if (it.o < len) tma_tile2d_g2s(dst, &tmap, (s0 + it.seg) * STRIP, it.rr * C::ROWS_PER_UNIT, full, pol);
+                    TRACE(8, lane == 0 && n == 0);
+                    it.advance(SU, R);
+                    full += 8; empty += 8; dst += C::STAGE_BYTES;
+                    if (++s == nstage) {
+                        s = 0;
+                        full = bar_u32; empty = bar_u32 + 128; dst = stage_u32 + lane * C::BOX_BYTES;
+                        if (refill) ph ^= 1u;
+                        refill = true;
                     }
                 }
-                tot += bytes[h];
             }
-            tot = __reduce_add_sync(0xffffffffu, tot);
-            if (lane == 0) mbar_expect_tx(full, tot);
-            __syncwarp();
-#pragma unroll
-            for (int h = 0; h < (COPIES + 31) / 32; ++h)
-                if (bytes[h]) tma_bulk_g2s(dst[h], src[h], bytes[h], full, pol);
+        } else {
+            constexpr int COPIES = SU * C::ROWS_PER_UNIT;  // 16 (w4) / 48 (w3) row copies per stage
+            for (int n = 0; n < nst; ++n) {
+                const int use = n / nstage, s = n - use * nstage;
+                const uint32_t full = bar_u32 + 8 * s, empty = bar_u32 + 128 + 8 * s;
+                if (use > 0) mbar_wait(empty, (use - 1) & 1);
+                // each lane describes up to 2 copies: copy id -> (unit, row-in-unit)
+                uint32_t bytes[2] = {0u, 0u}, dst[2] = {0u, 0u};
+                const uint32_t *src[2] = {nullptr, nullptr};
+                uint32_t tot = 0;
+    #pragma unroll
+                for (int h = 0; h < (COPIES + 31) / 32; ++h) {
+                    const int cid = lane + 32 * h;
+                    if (cid < COPIES) {
+                        const int u = cid / C::ROWS_PER_UNIT, rowin = cid - u * C::ROWS_PER_UNIT;
+                        const int o = n * SU + u;
+                        if (o < len) {
+                            UnitIt it;
+                            it.init(o, r0, R);
+                            const int c0 = (s0 + it.seg) * STRIP;
+                            bytes[h] = (uint32_t)min(STRIP, N - c0) * 4u;
+                            src[h] = p.qw + (size_t)(it.rr * C::ROWS_PER_UNIT + rowin) * N + c0;
+                            dst[h] = stage_u32 + s * C::STAGE_BYTES + cid * (STRIP * 4);
+                        }
+                    }
+                    tot += bytes[h];
+                }
+                tot = __reduce_add_sync(0xffffffffu, tot);
+                if (lane == 0) mbar_expect_tx(full, tot);
+                __syncwarp();
+    #pragma unroll
+                for (int h = 0; h < (COPIES + 31) / 32; ++h)
+                    if (bytes[h]) tma_bulk_g2s(dst[h], src[h], bytes[h], full, pol);
+                TRACE(8, lane == 0 && n == 0);
+            }
         }
+        TRACE(9, lane == 0);
     } else if (warp == WARP_SPARSE) {
         sparse_warp<BITS, FUSED>(p, sm, sm_u32, lane, nseg, s0, r0, csr_acc, srows, hyb_tot);
+        TRACE(10, lane == 0);
     } else {
         // ---- consumers: stage the LUTs of this CTA's strips, transposed to [value][slot]; 2-way conflicts at worst ----
         {
             const int c = tid & (STRIP - 1), vg = tid >> 6;
             const int slot = ((c & 3) << 4) | (c >> 2);
-            for (int seg = 0; seg < nseg; ++seg) {
+            for (int seg = 0; seg < ((p.dbg & 4) ? 0 : nseg); ++seg) {
                 const int col = (s0 + seg) * STRIP + c;
                 const uint32_t dst = sm_u32 + seg * C::TAB + slot * 4;
 #pragma unroll
-                for (int v = vg; v < C::L; v += 4) {
+                for (int v = vg; v < C::L; v += NW / 2) {
                     if (col < N) cp_async4(dst + v * (STRIP * 4), p.lut + (size_t)col * C::L + v);
                     else *reinterpret_cast<float *>(sm + seg * C::TAB + v * (STRIP * 4) + slot * 4) = 0.f;
                 }
             }
         }
-        for (int e = tid; e < MAXSEG * NW * STRIP; e += NW * 32) part[e] = 0.f;
+        for (int e = tid; e < maxseg * NW * STRIP; e += NW * 32) part[e] = 0.f;
 
-        pdl_wait();  // everything below reads data the previous kernel may have produced (x, mul, workspace)
+        TRACE(2, tid == 0);
+        // Everything below reads data the previous kernel may have produced (x, mul, workspace).  One thread waits on the
+        // programmatic dependency; the other consumers sleep on a hardware barrier instead of each polling it.
+#ifdef SQLLM_WAIT_ALL
+        pdl_wait();
+#else
+        if (tid == 0) pdl_wait();
+        named_bar_sync(6, NW * 32);
+#endif
+        TRACE(3, tid == 0);
 
         // ---- stage the slice(s) of x this CTA needs, as fp32 ----
         for (int seg = 0; seg < nseg; ++seg) {
@@ -675,25 +777,25 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
         cp_async_commit();
         cp_async_wait_all();
         named_bar_sync(5, NW * 32);  // consumers only: LUTs, x slice, zeroed partials visible
+        TRACE(4, tid == 0);
     }
 
     const int i16 = lane & 15, jsel = lane >> 4;
 
     if (warp < NW) {
         // =========================== consumer warps ===========================
+        // Everything in this loop is addressed through 32-bit shared-window addresses (no generic pointers: those make
+        // the compiler rematerialise the window base through S2UR inside the loop when registers are tight).
         uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
-        uint32_t ls[4] = {0u, 0u, 0u, 0u};
-        uint32_t segc = 0u;
+        uint32_t lsb = 0u, segc = 0u;
         int cur_seg = -1;
+        const uint32_t part_u32 = sm_u32 + C::off_part(maxseg) + (warp * STRIP + 4 * i16) * 4;
+        const uint32_t lane_slot = (uint32_t)((jsel << 6) | (i16 << 2));  // column 0 of this lane: slot ((0^jsel)<<4 | i16), x4 bytes
 
         auto set_seg = [&](int seg) {
             const uint32_t tb = sm_u32 + seg * C::TAB;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const uint32_t slot4 = ((((t ^ jsel) << 4) | i16) << 2);
-                if (BITS == 4) ls[t] = (tb & 0xFFFF0000u) | slot4;  // byte1 comes from the nibble | segc
-                else ls[t] = tb + slot4;                            // 2 KB aligned: bits 8..10 are free
-            }
+            // 4-bit: byte 1 of the address comes from the nibble | segc (table 4 KB aligned); 3-bit: bits 8..10 are free (2 KB aligned)
+            lsb = (BITS == 4 ? (tb & 0xFFFF0000u) : tb) | lane_slot;
             segc = ((tb >> 8) & 0xF0u) * 0x01010101u;
         };
         auto deposit = [&](int seg) {
@@ -706,30 +808,36 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
             const float v2 = __shfl_xor_sync(0xffffffffu, s[3], 16);
             const float v3 = __shfl_xor_sync(0xffffffffu, s[2], 16);
             if (jsel == 0)
-                *reinterpret_cast<float4 *>(part + (seg * NW + warp) * STRIP + 4 * i16) =
-                    make_float4(s[0] + v0, s[1] + v1, s[2] + v2, s[3] + v3);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(part_u32 + seg * (NW * STRIP * 4)), "f"(s[0] + v0),
+                             "f"(s[1] + v1), "f"(s[2] + v2), "f"(s[3] + v3) : "memory");
 #pragma unroll
             for (int t = 0; t < 4; ++t) acc[t] = 0ull;
         };
 
         // this lane's unit inside a stage: 2*warp + jsel ; its 16 bytes at column group i16
-        const uint32_t lane_off = (2 * warp + jsel) * C::UNIT_BYTES + i16 * 16;
+        const uint32_t lane_off = stage_u32 + (2 * warp + jsel) * C::UNIT_BYTES + i16 * 16;
+        const uint32_t xlane = xs_u32 + (C::XU * 4) * jsel;
+        const bool xdir = p.x_direct != 0;
         UnitIt it;
         it.init(2 * warp, r0, R);
         Words<BITS> cur = {}, nxt = {};
-        if (nst > 0) {
-            mbar_wait(bar_u32, 0);
-            load_words(cur, stage_u32 + lane_off);
+        int s = 0;               // ring slot of the stage being fetched
+        uint32_t par = 0;        // its phase parity
+        auto fetch = [&](Words<BITS> &dst) {  // wait for ring slot s, pull this lane's words, release the slot, advance
+            mbar_wait(bar_u32 + 8 * s, par);
+            load_words(dst, lane_off + s * C::STAGE_BYTES);
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_u32 + 64);
+            if (lane == 0) mbar_arrive(bar_u32 + 128 + 8 * s);
+            if (++s == nstage) { s = 0; par ^= 1u; }
+        };
+        if (nst > 0) {
+            fetch(cur);
+            TRACE(5, tid == 0);
         }
         for (int n = 0; n < nst; ++n) {
             if (n + 1 < nst) {  // pull the next stage into registers before computing on this one
-                const int s = (n + 1) % C::NSTAGE;
-                mbar_wait(bar_u32 + 8 * s, ((n + 1) / C::NSTAGE) & 1);
-                load_words(nxt, stage_u32 + s * C::STAGE_BYTES + lane_off);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_u32 + 64 + 8 * s);
+                fetch(nxt);
+                TRACE(16 + (n + 1 < 15 ? n + 1 : 15), tid == 0);
             }
             if (it.o < len) {  // warp-uniform: len and o are even, a pair never straddles the end
                 if (it.seg != cur_seg) {
@@ -737,16 +845,18 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
                     cur_seg = it.seg;
                     set_seg(cur_seg);
                 }
-                const int xunit = (p.x_direct ? it.rr : it.o) + jsel;
-                consume(cur, jsel, ls, segc, xs_u32 + (C::XU * 4) * xunit, acc);
+                if (!(p.dbg & 1)) consume(cur, jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
+                else acc[0] ^= cur.a.x;
             }
             it.advance(SU, R);
             cur = nxt;
         }
         if (cur_seg >= 0) deposit(cur_seg);
+        TRACE(6, tid == 0);
     }
 
     __syncthreads();  // all partials of this CTA are in shared memory
+    TRACE(7, tid == 0);
 
     // =========================== flush ===========================
     if (tid < MAXSEG * STRIP) {
@@ -764,6 +874,7 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
         if (!FUSED) {
             const int col = strip * STRIP + c;
             if (active && col < N) atomicAdd(reinterpret_cast<float *>(p.out) + col, tot);
+            TRACE(11, tid == 0);
             return;
         }
         if (active) {
@@ -801,6 +912,7 @@ __global__ void __launch_bounds__(THREADS) lutgemv_kernel(const Params p) {
             __threadfence();
             final_store(p, strip, c, nd, hyb);
         }
+        TRACE(11, tid == 0);
     }
 }
 
@@ -847,36 +959,61 @@ int fail(int code, const char *fmt, ...) {
 struct DevInfo {
     int sm = 0;
     bool attr_set = false;
-    int occ_key[2][2] = {{-1, -1}, {-1, -1}};
-    int occ_val[2][2] = {{0, 0}, {0, 0}};
 };
 DevInfo g_dev[64];
 int g_use_pdl = -1;
+int g_last_grid = 0;
+unsigned long long *g_trace = nullptr;
+size_t g_trace_stride = 0;
 
-template <int BITS, bool FUSED>
-int occupancy(int smem) {
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lutgemv_kernel<BITS, FUSED>, THREADS, smem);
-    return occ;
-}
-
-int query_occ(DevInfo &d, int bits, bool fused, int smem) {
-    const int bi = bits == 4 ? 1 : 0, fi = fused ? 1 : 0;
-    if (d.occ_key[bi][fi] != smem) {
-        d.occ_val[bi][fi] = bits == 4 ? (fused ? occupancy<4, true>(smem) : occupancy<4, false>(smem))
-                                      : (fused ? occupancy<3, true>(smem) : occupancy<3, false>(smem));
-        d.occ_key[bi][fi] = smem;
+// ---- 2-D tensor maps for the packed matrix (one per (pointer, shape, box)), created through the driver entry point ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TmKey {
+    const void *ptr; int rows, cols, box_rows;
+    bool operator==(const TmKey &o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+};
+struct TmHash {
+    size_t operator()(const TmKey &k) const {
+        return std::hash<const void *>()(k.ptr) ^ ((size_t)k.rows * 1000003u) ^ ((size_t)k.cols * 10007u) ^ (size_t)k.box_rows;
     }
-    return d.occ_val[bi][fi];
+};
+std::mutex g_tm_mutex;
+std::unordered_map<TmKey, CUtensorMap, TmHash> g_tm_cache;
+EncodeTiledFn g_encode = nullptr;
+
+int get_tensor_map(const void *qweight, int rows, int cols, int box_rows, CUtensorMap &out) {
+    std::lock_guard<std::mutex> lock(g_tm_mutex);
+    const TmKey key{qweight, rows, cols, box_rows};
+    auto it = g_tm_cache.find(key);
+    if (it != g_tm_cache.end()) { out = it->second; return SQLLM_OK; }
+    if (!g_encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+            return fail(SQLLM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)STRIP, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    const CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<void *>(qweight), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SQLLM_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    if (g_tm_cache.size() > 8192) g_tm_cache.clear();
+    g_tm_cache.emplace(key, m);
+    out = m;
+    return SQLLM_OK;
 }
 
 struct Plan {
-    int R, strips, T, chunk, G, maxc, hc, hrows, smem, maxseg, x_direct, xfloats;
+    int R, strips, T, chunk, G, maxc, hc, hrows, smem, maxseg, nstage, x_direct, xfloats, tma2d, box_rows;
     size_t ws_cnt_off, ws_hybcnt_off, ws_hyb_off, ws_part_off, ws_bytes;
 };
-
-template <int BITS>
-int smem_for(int maxseg, int xfloats, bool csr) { return Cfg<BITS>::total(maxseg, xfloats, csr); }
 
 int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &pl) {
     int dev = 0;
@@ -904,28 +1041,46 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &
     pl.T = (int)T;
     if (pl.strips > MAX_STRIPS) return fail(SQLLM_EINVAL, "out_features=%d exceeds the %d-strip workspace header", N, MAX_STRIPS);
 
-    // The grid depends on occupancy, occupancy on shared memory, shared memory on the chunk (x slice): iterate to a
-    // fixed point starting from the leanest guess (2 strips per CTA, compact x).
-    int occ = 1, chunk = 2, maxseg = 2, xfl = 0, smem = 0;
-    for (int iter = 0; iter < 4; ++iter) {
-        const int G0 = d.sm * occ;
-        chunk = (int)(2 * ((T + 2LL * G0 - 1) / (2LL * G0)));
-        if (chunk > 3 * pl.R) chunk = 3 * pl.R;  // a CTA may touch at most MAXSEG strips
-        if (chunk < 2) chunk = 2;
-        maxseg = (chunk - 2) / pl.R + 2;          // worst case over start offsets (even offsets, even R)
-        if (maxseg > MAXSEG) maxseg = MAXSEG;
-        const bool direct = (long long)chunk * XU >= K;
-        xfl = direct ? K : chunk * XU;
-        pl.x_direct = direct ? 1 : 0;
-        smem = bits == 4 ? smem_for<4>(maxseg, xfl, has_csr) : smem_for<3>(maxseg, xfl, has_csr);
-        if (smem > 227 * 1024) return fail(SQLLM_EINVAL, "in_features=%d needs %d B of shared memory (> 227 KB)", K, smem);
-        const int o = query_occ(d, bits, fused, smem);
-        if (o <= 0) return fail(SQLLM_ECUDA, "kernel cannot be resident (smem %d B)", smem);
-        if (o == occ && iter > 0) break;
-        occ = o;
+    // Each kernel takes only CPS CTA slots per SM (default 2 of the 4 that fit): the rest of the SM is left to the NEXT
+    // GEMV in the stream, which - launched with programmatic dependent launch - streams its weights into shared memory
+    // while this one is still computing.  All of a CTA's shared memory beyond the fixed part holds weight stages.
+    static int cps = 0, budget = 0;
+    if (!cps) {
+        const char *e1 = getenv("SQLLM_CTAS_PER_SM"), *e2 = getenv("SQLLM_SMEM_BUDGET_KB");
+        cps = e1 ? atoi(e1) : 2;
+        if (cps < 1 || cps > 8) cps = 2;
+        budget = (e2 ? atoi(e2) : 56) * 1024;
+        if (budget < 16 * 1024 || budget > 227 * 1024) budget = 56 * 1024;
     }
+    const int G0 = d.sm * cps;
+    // 2-D TMA boxes need every box inside one strip and one CTA range: units per box BU divides R and the chunk.
+    const int BU = bits == 4 ? Cfg<4>::BU : Cfg<3>::BU;
+    static int no_tma2d = -1;
+    if (no_tma2d < 0) { const char *e = getenv("SQLLM_NO_TMA2D"); no_tma2d = (e && e[0] == '1') ? 1 : 0; }
+    pl.tma2d = (!no_tma2d && K % 128 == 0 && pl.R % BU == 0) ? 1 : 0;
+    pl.box_rows = bits == 4 ? Cfg<4>::BOX_ROWS : Cfg<3>::BOX_ROWS;
+    const int gran = pl.tma2d ? (BU % 2 ? 2 * BU : BU) : 2;
+    int chunk = (int)(gran * ((T + (long long)gran * G0 - 1) / ((long long)gran * G0)));
+    if (chunk > 3 * pl.R) chunk = 3 * pl.R;  // a CTA may touch at most MAXSEG strips
+    if (chunk < 2) chunk = 2;
+    int maxseg = (chunk - 2) / pl.R + 2;      // worst case over start offsets (even offsets, even R)
+    if (maxseg > MAXSEG) maxseg = MAXSEG;
+    const bool direct = (long long)chunk * XU >= K;
+    const int xfl = direct ? K : chunk * XU;
+    pl.x_direct = direct ? 1 : 0;
+    const int stage_bytes = bits == 4 ? Cfg<4>::STAGE_BYTES : Cfg<3>::STAGE_BYTES;
+    const int fixed = bits == 4 ? Cfg<4>::total(maxseg, xfl, has_csr, 0) : Cfg<3>::total(maxseg, xfl, has_csr, 0);
+    const int need = (chunk + SU - 1) / SU;
+    int nstage = (budget - fixed) / stage_bytes;
+    if (nstage > need) nstage = need;
+    if (nstage > MAX_NSTAGE) nstage = MAX_NSTAGE;
+    if (nstage < 2) nstage = 2;
+    const int smem = fixed + nstage * stage_bytes;
+    if (smem > 227 * 1024) return fail(SQLLM_EINVAL, "in_features=%d needs %d B of shared memory (> 227 KB)", K, smem);
+    (void)fused;
     pl.smem = smem;
     pl.maxseg = maxseg;
+    pl.nstage = nstage;
     pl.xfloats = xfl;
     pl.chunk = chunk;
     pl.G = (int)((T + chunk - 1) / chunk);
@@ -963,13 +1118,14 @@ int check_common(const sqllm_lutgemv_args *a) {
 }
 
 template <int BITS, bool FUSED>
-cudaError_t launch_kernel(const Plan &pl, const Params &p, cudaStream_t st) {
+cudaError_t launch_kernel(const Plan &pl, const Params &p, const CUtensorMap &tm, cudaStream_t st) {
     if (g_use_pdl < 0) {
         const char *e = getenv("SQLLM_NO_PDL");
         g_use_pdl = (e && e[0] == '1') ? 0 : 1;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
+    g_last_grid = pl.G;
     cfg.gridDim = dim3(pl.G);
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = pl.smem;
@@ -979,7 +1135,7 @@ cudaError_t launch_kernel(const Plan &pl, const Params &p, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, lutgemv_kernel<BITS, FUSED>, p);
+    return cudaLaunchKernelEx(&cfg, lutgemv_kernel<BITS, FUSED>, p, tm);
 }
 
 template <bool FUSED>
@@ -993,10 +1149,19 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
     p.topX = hyb ? a->topX : 0;
     p.K = a->in_features; p.N = a->out_features;
     p.R = pl.R; p.strips = pl.strips; p.T = pl.T; p.chunk = pl.chunk;
-    p.maxseg = pl.maxseg; p.x_direct = pl.x_direct; p.xfloats = pl.xfloats;
+    p.maxseg = pl.maxseg; p.nstage = pl.nstage; p.tma2d = pl.tma2d; p.x_direct = pl.x_direct; p.xfloats = pl.xfloats;
     p.hc = hyb ? pl.hc : 0; p.hrows = pl.hrows; p.maxc = pl.maxc;
     p.has_csr = a->rows ? 1 : 0;
-    const cudaError_t e = a->bits == 4 ? launch_kernel<4, FUSED>(pl, p, st) : launch_kernel<3, FUSED>(pl, p, st);
+    p.trace = g_trace;
+    { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SQLLM_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+    if (g_trace) g_trace += g_trace_stride;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (pl.tma2d) {
+        const int rc = get_tensor_map(a->qweight, a->in_features / 32 * a->bits, a->out_features, pl.box_rows, tm);
+        if (rc) return rc;
+    }
+    const cudaError_t e = a->bits == 4 ? launch_kernel<4, FUSED>(pl, p, tm, st) : launch_kernel<3, FUSED>(pl, p, tm, st);
     if (e != cudaSuccess) return fail(SQLLM_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return SQLLM_OK;
 }
@@ -1009,6 +1174,10 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
 extern "C" {
 
 int sqllm_abi_version(void) { return SQLLM_ABI_VERSION; }
+
+// debug hook (not in the public header): successive launches write their timeline at buf, buf+stride, ...
+void sqllm_debug_set_trace(unsigned long long *buf, size_t stride_words) { g_trace = buf; g_trace_stride = stride_words; }
+int sqllm_debug_last_grid(void) { return g_last_grid; }
 const char *sqllm_last_error(void) { return g_err; }
 
 int sqllm_device_sm_count(void) {

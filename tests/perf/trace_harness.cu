@@ -1,0 +1,94 @@
+// trace_harness.cu - timeline of a chain of back-to-back GEMVs (C ABI, PDL, CUDA graph).  Links a -DSQLLM_TRACE build of
+// lutgemv_kernels.cu.  Prints, per launch, min/max over CTAs of each phase stamp relative to the chain start (ns).
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -DSQLLM_TRACE -I include -o trace_harness \
+//        tests/perf/trace_harness.cu squeezellm_b200/csrc/lutgemv_kernels.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "sqllm_b200.h"
+extern "C" void sqllm_debug_set_trace(unsigned long long *buf, size_t stride_words);
+extern "C" int sqllm_debug_last_grid(void);
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+int main(int argc, char **argv) {
+    setvbuf(stdout, NULL, _IONBF, 0);
+    const int bits = argc > 1 ? atoi(argv[1]) : 4, K = argc > 2 ? atoi(argv[2]) : 4096, N = argc > 3 ? atoi(argv[3]) : 4096;
+    const int chain = argc > 4 ? atoi(argv[4]) : 12, use_graph = argc > 5 ? atoi(argv[5]) : 1;
+    const size_t qwords = (size_t)K / 32 * bits * N;
+    const int copies = (size_t)K * N > (64u << 20) ? 3 : 40;
+    uint32_t *q; float *lut, *x, *y; unsigned long long *trace;
+    CK(cudaMalloc(&q, qwords * 4 * copies)); CK(cudaMemset(q, 0x5a, qwords * 4 * copies));
+    CK(cudaMalloc(&lut, (size_t)N * 16 * 4)); CK(cudaMemset(lut, 0, (size_t)N * 16 * 4));
+    CK(cudaMalloc(&x, K * 4)); CK(cudaMemset(x, 0, K * 4));
+    CK(cudaMalloc(&y, (size_t)N * 4 * chain)); CK(cudaMemset(y, 0, (size_t)N * 4 * chain));
+    const size_t stride = 1024 * 32;
+    CK(cudaMalloc(&trace, stride * 8 * chain)); CK(cudaMemset(trace, 0, stride * 8 * chain));
+    cudaStream_t st; CK(cudaStreamCreate(&st));
+    auto run_chain = [&](bool tr) {
+        sqllm_debug_set_trace(tr ? trace : nullptr, tr ? stride : 0);
+        for (int i = 0; i < chain; ++i) {
+            sqllm_lutgemv_args a; memset(&a, 0, sizeof(a));
+            a.bits = bits; a.in_features = K; a.out_features = N; a.batch = 1;
+            a.qweight = (const int32_t *)(q + (size_t)(i % copies) * qwords); a.lookup_table = lut; a.vec = x; a.mul = y + (size_t)i * N;
+            int rc = sqllm_lutgemv(&a, st);
+            if (rc) { printf("error: %s\n", sqllm_last_error()); exit(1); }
+        }
+    };
+    cudaGraphExec_t exec = nullptr;
+    run_chain(false); CK(cudaStreamSynchronize(st));
+    if (use_graph) {
+        cudaGraph_t g;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal));
+        run_chain(true);
+        CK(cudaStreamEndCapture(st, &g));
+        CK(cudaGraphInstantiate(&exec, g, 0));
+    }
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e9f;
+    for (int r = 0; r < 6; ++r) {
+        // flush L2 between chains so that weights come from HBM
+        CK(cudaMemsetAsync(q + (size_t)(copies - 1) * qwords, 0x5a, qwords * 4, st));
+        CK(cudaEventRecord(e0, st));
+        if (use_graph) CK(cudaGraphLaunch(exec, st)); else run_chain(true);
+        CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = std::min(best, ms);
+    }
+    const int G = sqllm_debug_last_grid();
+    printf("w%d %dx%d chain=%d graph=%d grid=%d : %.2f us per GEMV (best of 6 chains)\n", bits, K, N, chain, use_graph, G, best * 1e3 / chain);
+    std::vector<unsigned long long> h(stride * chain);
+    CK(cudaMemcpy(h.data(), trace, stride * 8 * chain, cudaMemcpyDeviceToHost));
+    unsigned long long t00 = ~0ull;
+    for (int c = 0; c < G; ++c) if (h[c * 32]) t00 = std::min(t00, h[c * 32]);
+    const char *names[12] = {"entry", "sync0", "pre-wait", "post-wait", "x-staged", "1st-full", "loop-end", "sync1", "tma-1st", "tma-last", "sparse", "exit"};
+    printf("%-4s", "k");
+    for (int s = 0; s < 12; ++s) printf(" %9s(min/max)", names[s]);
+    printf("\n");
+    for (int i = 0; i < chain; ++i) {
+        printf("%-4d", i);
+        for (int s = 0; s < 12; ++s) {
+            unsigned long long mn = ~0ull, mx = 0;
+            for (int c = 0; c < G; ++c) { unsigned long long v = h[(size_t)i * stride + c * 32 + s]; if (v) { mn = std::min(mn, v); mx = std::max(mx, v); } }
+            if (mx) printf(" %8.2f/%8.2f", (mn - t00) / 1e3, (mx - t00) / 1e3); else printf(" %17s", "-");
+        }
+        printf("\n");
+    }
+    {   // per-CTA detail of a steady-state launch: smid, post-wait, per-stage ready times, loop-end, relative to that launch's min post-wait
+        const int i = chain - 2;
+        unsigned long long base = ~0ull;
+        for (int c = 0; c < G; ++c) { unsigned long long v = h[(size_t)i * stride + c * 32 + 3]; if (v) base = std::min(base, v); }
+        printf("launch %d per-CTA (us rel. to min post-wait): cta smid entry post-wait x-staged st0..st7 loop-end exit\n", i);
+        for (int c = 0; c < G; c += (G > 64 ? 7 : 1)) {
+            const unsigned long long *r = &h[(size_t)i * stride + c * 32];
+            auto rel = [&](unsigned long long v) { return v ? ((double)v - (double)base) / 1e3 : -99.0; };
+            printf("%4d %4d %7.2f %6.2f %6.2f |", c, (int)r[12] - 1, rel(r[0]), rel(r[3]), rel(r[4]));
+            printf(" %6.2f", rel(r[5]));
+            for (int s2 = 1; s2 < 8; ++s2) printf(" %6.2f", rel(r[16 + s2]));
+            printf(" | %6.2f %6.2f\n", rel(r[6]), rel(r[11]));
+        }
+    }
+    return 0;
+}

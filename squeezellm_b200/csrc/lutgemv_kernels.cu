@@ -47,16 +47,27 @@ namespace {
 #ifndef SQLLM_NW
 #define SQLLM_NW 8
 #endif
+#ifndef SQLLM_LDG
+#define SQLLM_LDG 2   // 2: per-thread private cp.async ring in shared memory (default); 1: LDG.128 register ring; 0: TMA producer warp + mbarrier ring
+#endif
 #ifndef SQLLM_MINB4
-#define SQLLM_MINB4 4
+#define SQLLM_MINB4 (SQLLM_LDG == 1 ? 3 : 4)   // resident CTAs per SM the register budget must allow
 #endif
 #ifndef SQLLM_MINB3
 #define SQLLM_MINB3 3
 #endif
+#ifndef SQLLM_PF4
+#define SQLLM_PF4 8   // 128-bit loads in flight per lane, 4-bit path (LDG / cp.async modes)
+#endif
+#ifndef SQLLM_PF3
+#define SQLLM_PF3 3   // 3-row groups in flight per lane, 3-bit path (LDG / cp.async modes)
+#endif
+constexpr bool LDG_MODE = SQLLM_LDG != 0;   // no producer warp
+constexpr bool CPA_MODE = SQLLM_LDG == 2;   // weights staged by each consumer thread into its own cp.async ring
 constexpr int NW = SQLLM_NW;              // consumer warps per CTA (multiple of 8)
-constexpr int WARP_PRODUCER = NW;         // warp index of the TMA producer
-constexpr int WARP_SPARSE = NW + 1;       // warp index of the CSR / dense-row warp
-constexpr int THREADS = (NW + 2) * 32;
+constexpr int WARP_PRODUCER = LDG_MODE ? -1 : NW;            // warp index of the TMA producer (TMA mode only)
+constexpr int WARP_SPARSE = LDG_MODE ? NW : NW + 1;          // warp index of the CSR / dense-row warp
+constexpr int THREADS = (NW + (LDG_MODE ? 1 : 2)) * 32;
 constexpr int MAXSEG = 4;                 // strips a CTA may touch
 constexpr int STRIP = 64;                 // output columns per strip (16 lanes x 4 columns)
 constexpr int SU = 2 * NW;                // units per pipeline stage (one pair per consumer warp)
@@ -115,6 +126,10 @@ struct Cfg {
     static constexpr int BU = BITS == 4 ? SU : 4;
     static constexpr int BOX_ROWS = BU * ROWS_PER_UNIT;
     static constexpr int BOX_BYTES = BOX_ROWS * STRIP * 4;
+    // cp.async mode: every consumer thread owns PF slots of POS_BYTES (its 4 columns of one unit), laid out [slot][row-in-unit][thread]
+    static constexpr int PF = BITS == 4 ? SQLLM_PF4 : SQLLM_PF3;
+    static constexpr int POS_BYTES = ROWS_PER_UNIT * 16;
+    static constexpr int RING_BYTES = PF * NW * 32 * POS_BYTES;
     // layout: [tables maxseg*TAB][part maxseg][csr_acc][srows][misc][x][csr stage][weight stages ...]
     __host__ __device__ static int off_part(int maxseg) { return maxseg * TAB; }
     __host__ __device__ static int off_csr(int maxseg) { return off_part(maxseg) + maxseg * NW * STRIP * 4; }
@@ -127,7 +142,7 @@ struct Cfg {
         return (off_cstage(maxseg, xfloats) + (csr ? CSR_CH * 8 : 0) + 127) & ~127;
     }
     __host__ __device__ static int total(int maxseg, int xfloats, bool csr, int nstage) {
-        return 4096 + off_stage(maxseg, xfloats, csr) + nstage * STAGE_BYTES;
+        return 4096 + off_stage(maxseg, xfloats, csr) + (CPA_MODE ? RING_BYTES : nstage * STAGE_BYTES);
     }
 };
 
@@ -148,6 +163,12 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint4 ldg_stream(const void *p) {  // read-once weights: no L1 allocation
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -156,6 +177,8 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
     uint64_t r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -334,6 +357,14 @@ __device__ __forceinline__ void consume(const Words<3> &g, const int jsel, const
 #pragma unroll
     for (int t = 0; t < 4; ++t) consume3_col(a[t], b[t], c[t], lsb ^ (uint32_t)(t << 6), xp, acc[t]);
 }
+__device__ __forceinline__ void gload_words(Words<4> &g, const uint32_t *q, size_t) { g.a = ldg_stream(q); }
+__device__ __forceinline__ void gload_words(Words<3> &g, const uint32_t *q, size_t N) {
+    g.a = ldg_stream(q);
+    g.b = ldg_stream(q + N);
+    g.c = ldg_stream(q + 2 * N);
+}
+__device__ __forceinline__ void zero_words(Words<4> &g) { g.a = make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ void zero_words(Words<3> &g) { g.a = g.b = g.c = make_uint4(0u, 0u, 0u, 0u); }
 __device__ __forceinline__ void load_words(Words<4> &g, uint32_t unit_addr) { g.a = lds_u4(unit_addr); }
 __device__ __forceinline__ void load_words(Words<3> &g, uint32_t unit_addr) {
     g.a = lds_u4(unit_addr);
@@ -641,7 +672,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
 #ifdef SQLLM_TRACE
     if (p.trace && tid == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); p.trace[(size_t)blockIdx.x * 32 + 12] = smid + 1; }
 #endif
-    if (tid == 0) {
+    if (!LDG_MODE && tid == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(bar_u32 + 8 * s, 1);          // full: the producer's arrive.expect_tx
             mbar_init(bar_u32 + 128 + 8 * s, NW);   // empty: one arrive per consumer warp
@@ -652,6 +683,45 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
     __syncthreads();
     TRACE(1, tid == 0);
 
+    // ---- LDG mode: the first PF packed-word loads of every lane go out before anything else.  They do not depend on the
+    //      previous kernel, so under PDL the register file of the next GEMV fills while this SM is still busy. ----
+    constexpr int PF = LDG_MODE ? C::PF : 1;
+    Words<BITS> ring[(LDG_MODE && !CPA_MODE) ? PF : 1];
+    UnitIt ld;
+    ld.init(2 * warp, r0, R);
+    auto gload = [&](Words<BITS> &w) {  // fetch the pair `ld` points at (this lane's unit and 4 columns), then advance
+        const int col0 = (s0 + ld.seg) * STRIP + 4 * (lane & 15);
+        if (ld.o < len && col0 < N) gload_words(w, p.qw + (size_t)((ld.rr + (lane >> 4)) * C::ROWS_PER_UNIT) * N + col0, (size_t)N);
+        else zero_words(w);
+        ld.advance(SU, R);
+    };
+    // cp.async mode: slot u of this thread lives at ring_u32 + ((u * ROWS_PER_UNIT + row) * NW*32 + tid) * 16 (consecutive threads are
+    // contiguous: coalesced fills, conflict-free 128-bit reads).  Exactly one group is committed per position, valid or not,
+    // so "at most PF-1 groups pending" always means "the oldest position has landed".
+    const uint32_t ring_u32 = stage_u32 + tid * 16;
+    auto cpa_issue = [&](int u) {
+        const int col0 = (s0 + ld.seg) * STRIP + 4 * (lane & 15);
+        const uint32_t dst = ring_u32 + u * (C::ROWS_PER_UNIT * NW * 32 * 16);
+        if (ld.o < len && col0 < N) {
+            const uint32_t *q = p.qw + (size_t)((ld.rr + (lane >> 4)) * C::ROWS_PER_UNIT) * N + col0;
+#pragma unroll
+            for (int r = 0; r < C::ROWS_PER_UNIT; ++r) cp_async16(dst + r * (NW * 32 * 16), q + (size_t)r * N);
+        } else {
+#pragma unroll
+            for (int r = 0; r < C::ROWS_PER_UNIT; ++r)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst + r * (NW * 32 * 16)), "r"(0u) : "memory");
+        }
+        cp_async_commit();
+        ld.advance(SU, R);
+    };
+    auto cpa_fetch = [&](Words<BITS> &w, int u) {
+        const uint32_t src = ring_u32 + u * (C::ROWS_PER_UNIT * NW * 32 * 16);
+        w.a = lds_u4(src);
+        if constexpr (BITS == 3) {
+            w.b = lds_u4(src + NW * 32 * 16);
+            w.c = lds_u4(src + 2 * NW * 32 * 16);
+        }
+    };
     if (warp == WARP_PRODUCER) {
         // =========================== TMA producer ===========================
         // Weights never depend on the previous kernel, so this runs ahead of pdl_wait().
@@ -725,6 +795,14 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         sparse_warp<BITS, FUSED>(p, sm, sm_u32, lane, nseg, s0, r0, csr_acc, srows, hyb_tot);
         TRACE(10, lane == 0);
     } else {
+        // ---- LDG mode: the first PF packed-word loads of every lane go out before anything else ----
+        if (CPA_MODE) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) cpa_issue(u);
+        } else if (LDG_MODE) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) gload(ring[u]);
+        }
         // ---- consumers: stage the LUTs of this CTA's strips, transposed to [value][slot]; 2-way conflicts at worst ----
         {
             const int c = tid & (STRIP - 1), vg = tid >> 6;
@@ -814,42 +892,83 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
             for (int t = 0; t < 4; ++t) acc[t] = 0ull;
         };
 
-        // this lane's unit inside a stage: 2*warp + jsel ; its 16 bytes at column group i16
-        const uint32_t lane_off = stage_u32 + (2 * warp + jsel) * C::UNIT_BYTES + i16 * 16;
         const uint32_t xlane = xs_u32 + (C::XU * 4) * jsel;
         const bool xdir = p.x_direct != 0;
         UnitIt it;
         it.init(2 * warp, r0, R);
-        Words<BITS> cur = {}, nxt = {};
-        int s = 0;               // ring slot of the stage being fetched
-        uint32_t par = 0;        // its phase parity
-        auto fetch = [&](Words<BITS> &dst) {  // wait for ring slot s, pull this lane's words, release the slot, advance
-            mbar_wait(bar_u32 + 8 * s, par);
-            load_words(dst, lane_off + s * C::STAGE_BYTES);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_u32 + 128 + 8 * s);
-            if (++s == nstage) { s = 0; par ^= 1u; }
-        };
-        if (nst > 0) {
-            fetch(cur);
-            TRACE(5, tid == 0);
-        }
-        for (int n = 0; n < nst; ++n) {
-            if (n + 1 < nst) {  // pull the next stage into registers before computing on this one
-                fetch(nxt);
-                TRACE(16 + (n + 1 < 15 ? n + 1 : 15), tid == 0);
-            }
-            if (it.o < len) {  // warp-uniform: len and o are even, a pair never straddles the end
-                if (it.seg != cur_seg) {
-                    if (cur_seg >= 0) deposit(cur_seg);
-                    cur_seg = it.seg;
-                    set_seg(cur_seg);
+        if constexpr (CPA_MODE) {
+            // private cp.async ring: wait until slot u has landed, pull it into registers, refill the slot, then do the math
+            while (it.o < len) {
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    if (it.o < len) {  // warp-uniform: len and o are even, a pair never straddles the end
+                        cp_async_wait_pending<PF - 1>();
+                        Words<BITS> cur;
+                        cpa_fetch(cur, u);
+                        if (it.seg != cur_seg) {
+                            if (cur_seg >= 0) deposit(cur_seg);
+                            cur_seg = it.seg;
+                            set_seg(cur_seg);
+                        }
+                        if (!(p.dbg & 1)) consume(cur, jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
+                        else acc[0] ^= cur.a.x;
+                        cpa_issue(u);  // the words are in registers (consumed above), the slot can be overwritten
+                        it.advance(SU, R);
+                    }
                 }
-                if (!(p.dbg & 1)) consume(cur, jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
-                else acc[0] ^= cur.a.x;
             }
-            it.advance(SU, R);
-            cur = nxt;
+        } else if constexpr (LDG_MODE) {
+            // register ring: consume slot u, immediately refill it with the pair PF positions ahead
+            while (it.o < len) {
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    if (it.o < len) {  // warp-uniform: len and o are even, a pair never straddles the end
+                        if (it.seg != cur_seg) {
+                            if (cur_seg >= 0) deposit(cur_seg);
+                            cur_seg = it.seg;
+                            set_seg(cur_seg);
+                        }
+                        if (!(p.dbg & 1)) consume(ring[u], jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
+                        else acc[0] ^= ring[u].a.x;
+                        gload(ring[u]);
+                        it.advance(SU, R);
+                    }
+                }
+            }
+        } else {
+            // this lane's unit inside a stage: 2*warp + jsel ; its 16 bytes at column group i16
+            const uint32_t lane_off = stage_u32 + (2 * warp + jsel) * C::UNIT_BYTES + i16 * 16;
+            Words<BITS> cur = {}, nxt = {};
+            int s = 0;               // ring slot of the stage being fetched
+            uint32_t par = 0;        // its phase parity
+            auto fetch = [&](Words<BITS> &dst) {  // wait for ring slot s, pull this lane's words, release the slot, advance
+                mbar_wait(bar_u32 + 8 * s, par);
+                load_words(dst, lane_off + s * C::STAGE_BYTES);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_u32 + 128 + 8 * s);
+                if (++s == nstage) { s = 0; par ^= 1u; }
+            };
+            if (nst > 0) {
+                fetch(cur);
+                TRACE(5, tid == 0);
+            }
+            for (int n = 0; n < nst; ++n) {
+                if (n + 1 < nst) {  // pull the next stage into registers before computing on this one
+                    fetch(nxt);
+                    TRACE(16 + (n + 1 < 15 ? n + 1 : 15), tid == 0);
+                }
+                if (it.o < len) {  // warp-uniform: len and o are even, a pair never straddles the end
+                    if (it.seg != cur_seg) {
+                        if (cur_seg >= 0) deposit(cur_seg);
+                        cur_seg = it.seg;
+                        set_seg(cur_seg);
+                    }
+                    if (!(p.dbg & 1)) consume(cur, jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
+                    else acc[0] ^= cur.a.x;
+                }
+                it.advance(SU, R);
+                cur = nxt;
+            }
         }
         if (cur_seg >= 0) deposit(cur_seg);
         TRACE(6, tid == 0);
@@ -1047,8 +1166,8 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &
     static int cps = 0, budget = 0;
     if (!cps) {
         const char *e1 = getenv("SQLLM_CTAS_PER_SM"), *e2 = getenv("SQLLM_SMEM_BUDGET_KB");
-        cps = e1 ? atoi(e1) : 2;
-        if (cps < 1 || cps > 8) cps = 2;
+        cps = e1 ? atoi(e1) : (LDG_MODE ? 3 : 2);
+        if (cps < 1 || cps > 8) cps = LDG_MODE ? 3 : 2;
         budget = (e2 ? atoi(e2) : 56) * 1024;
         if (budget < 16 * 1024 || budget > 227 * 1024) budget = 56 * 1024;
     }
@@ -1057,7 +1176,7 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &
     const int BU = bits == 4 ? Cfg<4>::BU : Cfg<3>::BU;
     static int no_tma2d = -1;
     if (no_tma2d < 0) { const char *e = getenv("SQLLM_NO_TMA2D"); no_tma2d = (e && e[0] == '1') ? 1 : 0; }
-    pl.tma2d = (!no_tma2d && K % 128 == 0 && pl.R % BU == 0) ? 1 : 0;
+    pl.tma2d = (!LDG_MODE && !no_tma2d && K % 128 == 0 && pl.R % BU == 0) ? 1 : 0;
     pl.box_rows = bits == 4 ? Cfg<4>::BOX_ROWS : Cfg<3>::BOX_ROWS;
     const int gran = pl.tma2d ? (BU % 2 ? 2 * BU : BU) : 2;
     int chunk = (int)(gran * ((T + (long long)gran * G0 - 1) / ((long long)gran * G0)));
@@ -1075,6 +1194,7 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &
     if (nstage > need) nstage = need;
     if (nstage > MAX_NSTAGE) nstage = MAX_NSTAGE;
     if (nstage < 2) nstage = 2;
+    if (LDG_MODE) nstage = 0;  // weights go straight to registers
     const int smem = fixed + nstage * stage_bytes;
     if (smem > 227 * 1024) return fail(SQLLM_EINVAL, "in_features=%d needs %d B of shared memory (> 227 KB)", K, smem);
     (void)fused;

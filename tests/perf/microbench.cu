@@ -148,51 +148,17 @@ int main() {
     const size_t bytes = 1ull << 30;
     uint32_t *q; CK(cudaMalloc(&q, bytes)); CK(cudaMemset(q, 1, bytes));
 
-    {   // flat read upper bound
-        const size_t n4 = bytes / 16;
-        for (int occ : {2, 4, 8}) {
-            float ms = time_ms([&] { flat_kernel<8><<<sms * occ, 256>>>((const uint4 *)q, n4, dout); }, 5);
-            printf("flat read   U=8 CTAs/SM=%d : %.1f GB/s\n", occ, bytes / ms / 1e6);
-        }
-    }
-    // streamed matrices: many distinct matrices back to back inside one launch would hide launch cost; here one big matrix
-    // rows x N with N = 4096 / 11008 and rows chosen to fill the 1 GiB buffer (per-launch bytes >> L2)
-    for (int N : {4096, 11008}) {
+    {   // does reserving shared memory (smaller L1) or extra idle warps slow the LDG stream?
+        const int N = 4096;
         const int rows = (int)(bytes / 4 / N) / 16 * 16;
         const double mb = (double)rows * N * 4;
-#define RUN_STREAM(SW, UU, OCC, NWARP) { \
-            const int strips = N / SW; const long long T = (long long)strips * rows; const int G = sms * OCC; \
-            const int chunk = (int)((T + G - 1) / G); \
-            float ms = time_ms([&] { stream_kernel<SW, UU><<<G, NWARP * 32>>>(q, rows, N, chunk, (int)T, dout); }, 3); \
-            printf("stream N=%5d stripw=%3d U=%d CTAs/SM=%d warps=%2d : %.1f GB/s\n", N, SW, UU, OCC, NWARP, mb / ms / 1e6); }
-        RUN_STREAM(64, 4, 3, 8) RUN_STREAM(64, 8, 3, 8) RUN_STREAM(64, 4, 4, 16) RUN_STREAM(64, 8, 2, 16)
-        RUN_STREAM(128, 4, 3, 8) RUN_STREAM(128, 8, 3, 8)
-    }
-    // small-matrix regime: one 4096x4096 w4 matrix (8.4 MB) per launch, rotating over 64 copies (> L2)
-    {
-        const int N = 4096, rows = 512, copies = 64;
-        const size_t per = (size_t)rows * N;
-        for (int occ : {2, 3, 4}) {
-            const int strips = N / 64; const int T = strips * rows; const int G = sms * occ; const int chunk = (T + G - 1) / G;
-            float ms = time_ms([&] { for (int c = 0; c < copies; ++c) stream_kernel<64, 8><<<G, 256>>>(q + c * per, rows, N, chunk, T, dout); }, 3);
-            printf("stream 4096x4096(w4) per-launch, CTAs/SM=%d: %.2f us per launch, %.1f GB/s\n", occ, ms * 1e3 / copies, per * 4.0 * copies / ms / 1e6);
+        const int strips = N / 64; const long long T = (long long)strips * rows;
+        CK(cudaFuncSetAttribute(stream_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        for (int occ : {2, 3}) for (int smem_kb : {0, 16, 32, 48, 64, 72}) for (int threads : {256, 288}) {
+            const int G = sms * occ; const int chunk = (int)((T + G - 1) / G);
+            float ms = time_ms([&] { stream_kernel<64, 6><<<G, threads, smem_kb * 1024>>>(q, rows, N, chunk, (int)T, dout); }, 3);
+            printf("stream U=6 CTAs/SM=%d threads=%d smem/CTA=%3d KB : %.1f GB/s\n", occ, threads, smem_kb, mb / ms / 1e6);
         }
     }
-    // lookup rate
-    for (int mode = 0; mode < 3; ++mode)
-        for (int occ : {1, 2, 3, 4})
-            for (int nw : {8, 16}) {
-                const int iters = 2000;
-                const int smem = 4096 + 4096 + 1024 + 256;
-                auto run = [&] {
-                    if (mode == 0) lookup_kernel<0><<<sms * occ, nw * 32, smem>>>(iters, (float *)dout);
-                    else if (mode == 1) lookup_kernel<1><<<sms * occ, nw * 32, smem>>>(iters, (float *)dout);
-                    else lookup_kernel<2><<<sms * occ, nw * 32, smem>>>(iters, (float *)dout);
-                };
-                float ms = time_ms(run, 3);
-                const double weights = (double)sms * occ * nw * 32 * 32.0 * iters;
-                printf("lookup mode=%d CTAs/SM=%d warps/CTA=%2d : %.2f Tweights/s = %.1f weights/clk/SM @%.2f GHz\n", mode, occ, nw,
-                       weights / ms / 1e9, weights / (ms * 1e-3) / sms / (clk * 1e3), clk / 1e6);
-            }
     return 0;
 }

@@ -90,8 +90,13 @@ int sqllm_lutgemv(const sqllm_lutgemv_args *args, void *stream);
 /* Fused module path behind QuantLinearLUT.forward (squeezellm/quant.py:211-312), batch-1 decode:
  *   y[c] = bias[c] + LUT-GEMV + CSR + dense rows, written (not accumulated) as fp16 or fp32,
  * from an fp16 or fp32 x, in ONE launch: replaces torch.zeros (quant.py:218), x.float() (:223,267),
- * the 1-3 reference launches and y.to(dtype) (:311).  Deterministic (fixed summation order).
+ * the 1-3 reference launches and y.to(dtype) (:311).  Summation order: see sqllm_set_deterministic.
  * x_is_half / y_is_half select the element type of x / y.  bias may be NULL. */
+/* Fused-path summation mode (process-wide).  0 (default, or env SQLLM_DETERMINISTIC unset): contributions are added with
+ * red.add.f32 into a scratch accumulator, like the reference's atomicAdd - results can differ in the last bits from run to run.
+ * 1: per-strip partials reduced in a fixed order by the last-arriving CTA - bit-reproducible, ~2x slower on sparse layers. */
+void sqllm_set_deterministic(int on);
+
 int sqllm_lutgemv_fused(const sqllm_lutgemv_args *args, /* vec/mul members ignored */
                         const void *x, int x_is_half, void *y, int y_is_half, const float *bias,
                         void *workspace, size_t workspace_bytes, void *stream);

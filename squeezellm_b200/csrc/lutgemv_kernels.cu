@@ -75,7 +75,9 @@ constexpr int CSR_CH = 1024;              // CSR elements staged per chunk
 constexpr int SROWS_LD = 68;              // padded row-pointer slice per segment (65 used)
 constexpr int MAX_TOPX_FUSED = 128;
 constexpr int MAX_STRIPS = 16320;         // per-strip tickets in the workspace header (out_features <= 1,044,480)
-constexpr size_t WS_HEADER = 65536;
+constexpr int MAX_N_FUSED = 262144;        // fused path: the scratch accumulator lives at a fixed place in the workspace
+constexpr size_t WS_ACC_OFF = 65536;       // [64 KB, 64 KB + 4*MAX_N_FUSED): fp32 accumulator (zero between launches)
+constexpr size_t WS_HEADER = WS_ACC_OFF + (size_t)MAX_N_FUSED * 4;  // tickets + accumulator: never shared with data of any shape
 constexpr int MAX_NSTAGE = 16;            // weight stages per CTA (runtime count, fills the shared-memory budget)
 
 struct Params {
@@ -108,6 +110,11 @@ struct Params {
     float *ws_hyb;    // [hc][topX]
     int *ws_hyb_cnt;  // [1]
     int has_csr;
+    int has_stage;   // shared-memory staging buffer present (CSR and / or dense rows)
+    int csr_rpc;     // CSR rows (output channels) handled per CTA: rows are spread evenly over all CTAs
+    float *ws_csr;   // [N] CSR row sums (deterministic fused mode)
+    float *ws_acc;   // [N] fp32 accumulator, zero between launches (fast fused mode)
+    int det;         // fused mode: 1 = deterministic per-strip tickets, 0 = red.add into ws_acc + one global ticket per CTA
     int dbg;                    // debug: 1 = skip the gather/FMA math, 2 = no work at all, 4 = skip LUT staging (SQLLM_DEBUG_FLAGS)
     unsigned long long *trace;  // debug timeline (only written when built with -DSQLLM_TRACE and non-null)
 };
@@ -136,10 +143,10 @@ struct Cfg {
     __host__ __device__ static int off_srows(int maxseg) { return off_csr(maxseg) + MAXSEG * STRIP * 4; }
     __host__ __device__ static int off_misc(int maxseg) { return off_srows(maxseg) + MAXSEG * SROWS_LD * 4; }
     // misc: 2 x MAX_NSTAGE mbarriers (256 B) + 16 ints (64 B) + float[MAX_TOPX_FUSED]
-    __host__ __device__ static int off_x(int maxseg) { return off_misc(maxseg) + 256 + 64 + MAX_TOPX_FUSED * 4; }
+    __host__ __device__ static int off_x(int maxseg) { return off_misc(maxseg) + 256 + 64 + (MAXSEG + 1) * MAX_TOPX_FUSED * 4; }
     __host__ __device__ static int off_cstage(int maxseg, int xfloats) { return off_x(maxseg) + ((xfloats * 4 + 15) & ~15); }
-    __host__ __device__ static int off_stage(int maxseg, int xfloats, bool csr) {
-        return (off_cstage(maxseg, xfloats) + (csr ? CSR_CH * 8 : 0) + 127) & ~127;
+    __host__ __device__ static int off_stage(int maxseg, int xfloats, bool csr) {  // csr: staging buffers present (CSR 8 KB + dense-row partials 8 KB)
+        return (off_cstage(maxseg, xfloats) + (csr ? CSR_CH * 16 : 0) + 127) & ~127;
     }
     __host__ __device__ static int total(int maxseg, int xfloats, bool csr, int nstage) {
         return 4096 + off_stage(maxseg, xfloats, csr) + (CPA_MODE ? RING_BYTES : nstage * STAGE_BYTES);
@@ -198,6 +205,20 @@ __device__ __forceinline__ float warp_sum(float v) {  // fixed xor tree -> deter
     return v;
 }
 __device__ __forceinline__ float ldcg_f32(const float *p) { return __ldcg(p); }
+// Ticket: one gpu-scope acq_rel atomic.  The release half publishes everything the calling thread wrote - and, by
+// cumulativity, what the threads it synchronised with (bar.sync / __syncwarp) wrote before that barrier; the acquire half makes
+// the other contributors' published partials visible to whoever draws the last ticket (and, through the next barrier, to its
+// whole group).  This replaces the fence / atomic / fence triple (~1 us per fence on a busy B200).
+__device__ __forceinline__ int ticket_take(int *counter) {
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    return old;
+}
+#if defined(SQLLM_TRACE) || defined(SQLLM_DEBUG)
+#define DBG(p) ((p).dbg)
+#else
+#define DBG(p) 0
+#endif
 #ifdef SQLLM_TRACE
 __device__ __forceinline__ void trace_mark(const Params &p, int slot) {
     if (p.trace) {
@@ -265,6 +286,23 @@ struct UnitIt {
         o += step;
         rr += step;
         while (rr >= R) { rr -= R; ++seg; }
+    }
+};
+
+// Walks, in order, the positions (unit pairs) one consumer warp owns: offset 2*warp + SU*p from the CTA's first unit.  Within a
+// segment (= strip) consecutive positions are SU units apart, so callers keep running pointers and only `seek` at segment ends.
+struct Cursor {
+    int seg;   // current segment; == nseg when exhausted
+    int left;  // positions left in this segment (including the current one)
+    int rr;    // unit index inside the strip of the current position (the lane adds its own 0/1)
+    __device__ __forceinline__ void seek(int from_seg, int warp2, int r0, int R, int len, int nseg) {
+        for (int sg = from_seg; sg < nseg; ++sg) {
+            const int b = sg == 0 ? 0 : sg * R - r0, e = min(len, (sg + 1) * R - r0);   // offsets [b, e) belong to segment sg
+            const int pf = b <= warp2 ? 0 : (b - warp2 + SU - 1) / SU;                   // first position with offset >= b
+            const int pl = e <= warp2 ? 0 : (e - warp2 + SU - 1) / SU;                   // positions with offset < e
+            if (pl > pf) { seg = sg; left = pl - pf; rr = warp2 + SU * pf + r0 - sg * R; return; }
+        }
+        seg = nseg; left = 0; rr = 0;
     }
 };
 
@@ -372,19 +410,7 @@ __device__ __forceinline__ void load_words(Words<3> &g, uint32_t unit_addr) {
     g.c = lds_u4(unit_addr + 2 * STRIP * 4);
 }
 
-// ---- per-column final reduction of a strip's workspace partials (fused mode) ----------------------
-__device__ __forceinline__ void final_store(const Params &p, int strip, int c, int nd, bool hyb) {
-    const int col = strip * STRIP + c;
-    if (col >= p.N) return;
-    const float *base = p.ws_part + (size_t)strip * (p.maxc + 1) * STRIP + c;
-    float tot = 0.f;
-    for (int s = 0; s < nd; ++s) tot += ldcg_f32(base + s * STRIP);
-    if (hyb) tot += ldcg_f32(base + p.maxc * STRIP);
-    if (p.bias) tot += p.bias[col];
-    if (p.y_is_half) reinterpret_cast<__half *>(p.out)[col] = __float2half_rn(tot);
-    else reinterpret_cast<float *>(p.out)[col] = tot;
-}
-
+// ---- fused mode: who contributes to a strip, and the per-column final reduction ----------------------
 __device__ __forceinline__ bool strip_has_hybrid(const Params &p, int strip) {
     if (!p.full_rows) return false;
     bool h = false;
@@ -394,26 +420,102 @@ __device__ __forceinline__ bool strip_has_hybrid(const Params &p, int strip) {
     }
     return h;
 }
+// Contributors that take a ticket on strip `strip` (deterministic fused mode): nd dense CTAs (stream-K), ncsr CTAs whose CSR row
+// range touches the strip and - if a dense row lands in it - all hc dense-row contributors.
+__device__ __forceinline__ int strip_contributors(const Params &p, int strip, int &nd, bool &hyb) {
+    const int first = (int)(((long long)strip * p.R) / p.chunk);
+    const int lastc = (int)((((long long)strip + 1) * p.R - 1) / p.chunk);
+    nd = lastc - first + 1;
+    hyb = strip_has_hybrid(p, strip);
+    int ncsr = 0;
+    if (p.rows) {
+        const int c0 = strip * STRIP, c1 = min(p.N, c0 + STRIP) - 1;
+        ncsr = c1 / p.csr_rpc - c0 / p.csr_rpc + 1;
+    }
+    return nd + ncsr + (hyb ? p.hc : 0);
+}
+// One warp: fixed-order totals of the dense-row partials ws_hyb[hc][topX] -> tot[topX] (shared memory).  All partials are
+// pulled through the staging buffer in one go (one latency), then lanes = (slot, j) sum contributors slot, slot+nsl, ... and the
+// slots are folded in fixed order: deterministic.  Callers guarantee every contributor has published (ticket) and fenced.
+__device__ __forceinline__ void hybrid_totals(const Params &p, uint32_t stage_u32, const float *stage, float *tot, int lane) {
+    const int tp = p.topX, tot_f = p.hc * tp;
+    const int n16 = tot_f >> 2;  // ws_hyb and the staging buffer are 16-byte aligned
+    for (int e = lane; e < n16; e += 32) cp_async16(stage_u32 + 16 * e, p.ws_hyb + 4 * e);
+    for (int e = 4 * n16 + lane; e < tot_f; e += 32) cp_async4(stage_u32 + 4 * e, p.ws_hyb + e);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncwarp();
+    const int nsl = tp <= 16 ? 32 / tp : 1;
+    for (int jb = 0; jb < (tp <= 16 ? 1 : tp); jb += 32) {
+        const int sl = tp <= 16 ? lane / tp : 0, j = tp <= 16 ? lane - sl * tp : jb + lane;
+        float t = 0.f;
+        if (sl < nsl && j < tp)
+            for (int b = sl; b < p.hc; b += nsl) t += stage[b * tp + j];
+        for (int q = 1; q < nsl; ++q) {
+            const float v = __shfl_sync(0xffffffffu, t, (j + q * tp) & 31);
+            if (sl == 0) t += v;
+        }
+        if (sl == 0 && j < tp) tot[j] = t;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void final_store(const Params &p, int strip, int c, int nd, const float *hyb_tot) {
+    const int col = strip * STRIP + c;
+    if (col >= p.N) return;
+    const float *base = p.ws_part + (size_t)strip * p.maxc * STRIP + c;
+    float tot = 0.f;
+    for (int s = 0; s < nd; ++s) tot += ldcg_f32(base + s * STRIP);
+    if (p.rows) tot += ldcg_f32(p.ws_csr + col);
+    if (hyb_tot)
+        for (int j = 0; j < p.topX; ++j)
+            if (__ldg(p.fri + j) == col) tot += hyb_tot[j];
+    if (p.bias) tot += p.bias[col];
+    if (p.y_is_half) reinterpret_cast<__half *>(p.out)[col] = __float2half_rn(tot);
+    else reinterpret_cast<float *>(p.out)[col] = tot;
+}
+// one warp takes a ticket on `strip` and, if it is the last contributor, reduces and stores the strip's 64 columns
+__device__ __forceinline__ void warp_ticket(const Params &p, int strip, int lane, uint32_t hstage_u32, const float *hstage, float *hyb_tot) {
+    int nd;
+    bool hyb;
+    const int expected = strip_contributors(p, strip, nd, hyb);
+    int fin = 0;
+    __syncwarp();
+    if (lane == 0) {
+        fin = (ticket_take(p.ws_cnt + strip) == expected - 1);
+        if (fin) p.ws_cnt[strip] = 0;
+    }
+    fin = __shfl_sync(0xffffffffu, fin, 0);
+    if (fin) {
+        if (hyb) hybrid_totals(p, hstage_u32, hstage, hyb_tot, lane);
+        final_store(p, strip, lane, nd, hyb ? hyb_tot : nullptr);
+        final_store(p, strip, lane + 32, nd, hyb ? hyb_tot : nullptr);
+    }
+}
 
-__device__ __forceinline__ float load_x(const Params &p, int k) {
-    return p.x_is_half ? __half2float(reinterpret_cast<const __half *>(p.x)[k]) : reinterpret_cast<const float *>(p.x)[k];
+__device__ __forceinline__ float load_x(const Params &p, int k) {  // read-only path: x stays in L1 across the gathers
+    return p.x_is_half ? __half2float(__ldg(reinterpret_cast<const __half *>(p.x) + k)) : __ldg(reinterpret_cast<const float *>(p.x) + k);
 }
 
 // =================================================================================================
-// Sparse warp: CSR outliers of the strips this CTA owns + a slice of the topX dense rows.
-// Everything that does not depend on the previous kernel (row pointers, cols/vals staging, the dense-row
-// values) is fetched BEFORE griddepcontrol.wait, so under PDL it overlaps the previous GEMV.
+// Sparse warp.  CSR rows (= output channels) are spread evenly over ALL CTAs (csr_rpc consecutive rows each, ~9 for a 4096-wide
+// layer) and so are the k-rows of the topX dense rows; each warp therefore has a few hundred elements at most and every
+// step is lane-parallel: row pointers live one-per-lane (shuffles / ballots instead of serial scans), cols/vals are staged
+// with cp.async, x is gathered in batches of independent loads, per-row sums are taken in storage order (deterministic).
+// Everything static (row pointers, cols/vals, dense-row values) is requested BEFORE griddepcontrol.wait.
+// Results: accumulate mode -> red.add on mul; fused mode -> ws_csr[row] / dense-row partials + a ticket on the strips touched.
 // =================================================================================================
 template <int BITS, bool FUSED>
-__device__ __forceinline__ void sparse_warp(const Params &p, unsigned char *sm, const uint32_t sm_u32, const int lane,
-                                            const int nseg, const int s0, const int r0, float *csr_acc, int *srows,
-                                            float *hyb_tot) {
+__device__ __forceinline__ void sparse_warp(const Params &p, unsigned char *sm, const uint32_t sm_u32, const int lane, float *hyb_tot,
+                                            const int nseg, const int s0) {
     using C = Cfg<BITS>;
-    const int N = p.N, R = p.R;
-    for (int e = lane; e < MAXSEG * STRIP; e += 32) csr_acc[e] = 0.f;
+    const int N = p.N;
+    const int cso = C::off_cstage(p.maxseg, p.xfloats);
+    int *scols = reinterpret_cast<int *>(sm + cso);
+    float *svals = reinterpret_cast<float *>(sm + cso + CSR_CH * 4);
+    const uint32_t scols_u32 = sm_u32 + cso, svals_u32 = scols_u32 + CSR_CH * 4;
 
     // ---------------- phase A: static data ----------------
-    constexpr int HYB_R = 8;
+    constexpr int HYB_R = 11;
     float hfr[HYB_R];
     const bool hyb_on = p.full_rows && (int)blockIdx.x < p.hc;
     const bool hyb_multi = hyb_on && p.topX <= 16;  // several k-rows per warp step: lane = (row slot, column j)
@@ -429,48 +531,32 @@ __device__ __forceinline__ void sparse_warp(const Params &p, unsigned char *sm, 
             hfr[i] = (rs < nsl && k < ke) ? __ldg(p.full_rows + (size_t)k * p.topX + hj) : 0.f;
         }
     }
-    const int cso = C::off_cstage(p.maxseg, p.xfloats);
-    int *scols = reinterpret_cast<int *>(sm + cso);
-    float *svals = reinterpret_cast<float *>(sm + cso + CSR_CH * 4);
-    const uint32_t scols_u32 = sm_u32 + cso, svals_u32 = scols_u32 + CSR_CH * 4;
-    auto chunk_end = [&](const int *sr, int nc, int cb) {  // largest ce with sr[ce]-sr[cb] <= CSR_CH (at least cb+1)
-        int ce = cb + 1;
-        while (ce < nc && sr[ce + 1] - sr[cb] <= CSR_CH) ++ce;
-        return ce;
-    };
-    auto stage = [&](int base, int cnt) {
+    // CSR: this CTA's rows [ra, rb) (rows are spread evenly over all CTAs), processed in groups of <= 31 rows / <= CSR_CH elements;
+    // the first group is pre-staged before the dependency wait
+    const int ra = p.rows ? min(N, (int)blockIdx.x * p.csr_rpc) : 0, rb = p.rows ? min(N, ra + p.csr_rpc) : 0;
+    int r = ra, rp = 0, m = 0, base = 0, cnt = 0;
+    auto group_begin = [&]() {  // row pointers one per lane, group size by ballot, then stage cols/vals
+        rp = __ldg(p.rows + min(r + lane, rb));
+        base = __shfl_sync(0xffffffffu, rp, 0);
+        const bool ok = lane <= min(31, rb - r) && rp - base <= CSR_CH;
+        m = __popc(__ballot_sync(0xffffffffu, ok)) - 1;  // rp is non-decreasing: the ok lanes are a prefix that includes lane 0
+        cnt = m > 0 ? __shfl_sync(0xffffffffu, rp, m) - base : 0;
         for (int e = lane; e < cnt; e += 32) {
             cp_async4(scols_u32 + 4 * e, p.cols + base + e);
             cp_async4(svals_u32 + 4 * e, p.vals + base + e);
         }
         cp_async_commit();
     };
-    int fseg = -1;
-    if (p.rows) {
-        for (int seg = 0; seg < nseg; ++seg) {
-            const bool owner = (seg > 0) || (r0 == 0);
-            if (!owner) continue;
-            if (fseg < 0) fseg = seg;
-            const int c0 = (s0 + seg) * STRIP;
-            const int nc = min(STRIP, N - c0);
-            for (int t = lane; t <= nc; t += 32) srows[seg * SROWS_LD + t] = __ldg(p.rows + c0 + t);
-        }
-        __syncwarp();
-        if (fseg >= 0) {  // pre-stage the first chunk
-            const int nc = min(STRIP, N - (s0 + fseg) * STRIP);
-            const int *sr = srows + fseg * SROWS_LD;
-            const int ce = chunk_end(sr, nc, 0);
-            const int cnt = sr[ce] - sr[0];
-            if (cnt <= CSR_CH) stage(sr[0], cnt);
-        }
-    }
+    if (r < rb) group_begin();
 
+    TRACE(13, lane == 0);
 #ifdef SQLLM_WAIT_ALL
     pdl_wait();
 #else
     if (lane == 0) pdl_wait();
     __syncwarp();
 #endif
+    TRACE(14, lane == 0);
 
     // ---------------- phase B: needs x (and, in fused mode, the workspace) ----------------
     // (1) topX dense rows: CTA b < hc takes k-rows [kb, ke)
@@ -480,11 +566,14 @@ __device__ __forceinline__ void sparse_warp(const Params &p, unsigned char *sm, 
             int j;
             if (hyb_multi) {
                 j = hj;
+                float hx[HYB_R];
 #pragma unroll
                 for (int i = 0; i < HYB_R; ++i) {
                     const int k = kb + rs + nsl * i;
-                    if (rs < nsl && k < ke) a += hfr[i] * load_x(p, k);
+                    hx[i] = (rs < nsl && k < ke) ? load_x(p, k) : 0.f;
                 }
+#pragma unroll
+                for (int i = 0; i < HYB_R; ++i) a += hfr[i] * hx[i];
                 for (int k = kb + rs + nsl * HYB_R; rs < nsl && k < ke; k += nsl)
                     a += __ldg(p.full_rows + (size_t)k * p.topX + hj) * load_x(p, k);
                 // fold the row slots onto slot 0 in fixed order
@@ -502,130 +591,92 @@ __device__ __forceinline__ void sparse_warp(const Params &p, unsigned char *sm, 
                 }
             }
             if (j < p.topX) {
-                if (FUSED) {
+                if (FUSED && p.det) {
                     p.ws_hyb[(size_t)blockIdx.x * p.topX + j] = a;
-                    __threadfence();
                 } else {
                     const int c = __ldg(p.fri + j);
-                    if (c >= 0 && c < N) atomicAdd(reinterpret_cast<float *>(p.out) + c, a);
-                }
-            }
-        }
-        if (FUSED) {
-            __syncwarp();
-            int last = 0;
-            if (lane == 0) {
-                __threadfence();
-                last = (atomicAdd(p.ws_hyb_cnt, 1) == p.hc - 1);
-            }
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-                __threadfence();
-                if (lane == 0) *p.ws_hyb_cnt = 0;
-                for (int j = 0; j < p.topX; ++j) {  // lanes stride over contributors, fixed xor tree -> deterministic
-                    float t = 0.f;
-#pragma unroll 4
-                    for (int b = lane; b < p.hc; b += 32) t += ldcg_f32(p.ws_hyb + (size_t)b * p.topX + j);
-                    t = warp_sum(t);
-                    if (lane == 0) hyb_tot[j] = t;
-                }
-                __syncwarp();
-                // hand one "hybrid slot" vector to every strip that owns a dense-row output channel
-                for (int j0 = 0; j0 < p.topX; ++j0) {
-                    const int cj0 = __ldg(p.fri + j0);
-                    if (cj0 < 0 || cj0 >= N) continue;
-                    const int strip = cj0 / STRIP;
-                    bool seen = false;
-                    for (int j = 0; j < j0; ++j) {
-                        const int cj = __ldg(p.fri + j);
-                        seen |= (cj >= 0 && cj < N && cj / STRIP == strip);
-                    }
-                    if (seen) continue;
-                    float v0 = 0.f, v1 = 0.f;  // columns lane, lane+32 of the strip
-                    for (int j = j0; j < p.topX; ++j) {
-                        const int cj = __ldg(p.fri + j);
-                        if (cj >= 0 && cj < N && cj / STRIP == strip) {
-                            const int cc = cj - strip * STRIP;
-                            if (cc == lane) v0 += hyb_tot[j];
-                            if (cc == lane + 32) v1 += hyb_tot[j];
-                        }
-                    }
-                    float *slot = p.ws_part + ((size_t)strip * (p.maxc + 1) + p.maxc) * STRIP;
-                    slot[lane] = v0;
-                    slot[lane + 32] = v1;
-                    __threadfence();
-                    __syncwarp();
-                    const int first = (int)(((long long)strip * R) / p.chunk);
-                    const int lastc = (int)((((long long)strip + 1) * R - 1) / p.chunk);
-                    const int nd = lastc - first + 1;
-                    int fin = 0;
-                    if (lane == 0) {
-                        __threadfence();
-                        fin = (atomicAdd(p.ws_cnt + strip, 1) == nd);  // nd dense contributors + this one
-                        if (fin) p.ws_cnt[strip] = 0;
-                    }
-                    fin = __shfl_sync(0xffffffffu, fin, 0);
-                    if (fin) {
-                        __threadfence();
-                        final_store(p, strip, lane, nd, true);
-                        final_store(p, strip, lane + 32, nd, true);
-                    }
+                    if (c >= 0 && c < N) atomicAdd((FUSED ? p.ws_acc : reinterpret_cast<float *>(p.out)) + c, a);
                 }
             }
         }
     }
+    TRACE(15, lane == 0);
 
-    // (2) CSR outliers: deterministic per-row sums into csr_acc (x gathered straight from global / L2)
-    if (p.rows) {
-        for (int seg = 0; seg < nseg; ++seg) {
-            const bool owner = (seg > 0) || (r0 == 0);
-            if (!owner) continue;
-            const int c0 = (s0 + seg) * STRIP;
-            const int nc = min(STRIP, N - c0);
-            const int *sr = srows + seg * SROWS_LD;
-            float *out = csr_acc + seg * STRIP;
-            int cb = 0;
-            while (cb < nc) {
-                const int base = sr[cb];
-                const int ce = chunk_end(sr, nc, cb);
-                const int cnt = sr[ce] - base;
-                if (cnt > CSR_CH) {  // one very long row: straight from global memory
-                    float a = 0.f;
-                    for (int e = base + lane; e < sr[cb + 1]; e += 32) a += __ldg(p.vals + e) * load_x(p, __ldg(p.cols + e));
-                    a = warp_sum(a);
-                    if (lane == 0) out[cb] = a;
-                    cb += 1;
-                    continue;
+    // (2) CSR outliers
+    float *const acc_out = FUSED ? p.ws_acc : reinterpret_cast<float *>(p.out);  // where red.add contributions go (non-deterministic modes)
+    auto emit = [&](int row, float v) {
+        if (FUSED && p.det) p.ws_csr[row] = v;
+        else atomicAdd(acc_out + row, v);
+    };
+    while (r < rb) {
+        if (m == 0) {  // a single row longer than the staging buffer: straight from global memory, whole warp
+            const int e1 = __shfl_sync(0xffffffffu, rp, 1);
+            float a = 0.f;
+            for (int e = base + lane; e < e1; e += 32) a += __ldg(p.vals + e) * load_x(p, __ldg(p.cols + e));
+            a = warp_sum(a);
+            if (lane == 0) emit(r, a);
+            r += 1;
+        } else {
+            cp_async_wait_all();
+            __syncwarp();
+            // products vals[e] * x[cols[e]] in place; gathers go out in batches of 8 independent loads per lane
+            for (int e0 = lane; e0 < cnt; e0 += 32 * 8) {
+                float xv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int e = e0 + 32 * j;
+                    xv[j] = e < cnt ? load_x(p, scols[e]) : 0.f;
                 }
-                if (!(seg == fseg && cb == 0)) stage(base, cnt);
-                cp_async_wait_all();
-                __syncwarp();
-                // the product vals[e] * x[cols[e]] replaces vals[e] in place (independent gathers: full MLP)
-                for (int e = lane; e < cnt; e += 32) svals[e] *= load_x(p, scols[e]);
-                __syncwarp();
-                // pass 1: one lane per short row, sequential sum in storage order (two interleaved chains)
-                for (int c = cb + lane; c < ce; c += 32) {
-                    const int a0 = sr[c] - base, a1 = sr[c + 1] - base;
-                    if (a1 - a0 <= 64) {
-                        float ea = 0.f, eb = 0.f;
-                        int e = a0;
-                        for (; e + 1 < a1; e += 2) { ea += svals[e]; eb += svals[e + 1]; }
-                        if (e < a1) ea += svals[e];
-                        out[c] = ea + eb;
-                    }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int e = e0 + 32 * j;
+                    if (e < cnt) svals[e] *= xv[j];
                 }
-                // pass 2: the whole warp on each long row
-                for (int c = cb; c < ce; ++c) {
-                    const int a0 = sr[c] - base, a1 = sr[c + 1] - base;
-                    if (a1 - a0 > 64) {
-                        float a = 0.f;
-                        for (int e = a0 + lane; e < a1; e += 32) a += svals[e];
-                        a = warp_sum(a);
-                        if (lane == 0) out[c] = a;
-                    }
+            }
+            __syncwarp();
+            // lane i < m owns row r+i: [a0, a1) in the staged arrays
+            const int a0 = rp - base, a1 = __shfl_down_sync(0xffffffffu, rp, 1) - base;
+            const int n = lane < m ? a1 - a0 : 0;
+            if (lane < m && n <= 64) {  // short row: sequential sum in storage order (two interleaved chains)
+                float ea = 0.f, eb = 0.f;
+                int e = a0;
+                for (; e + 1 < a1; e += 2) { ea += svals[e]; eb += svals[e + 1]; }
+                if (e < a1) ea += svals[e];
+                emit(r + lane, ea + eb);
+            }
+            unsigned longm = __ballot_sync(0xffffffffu, n > 64);  // long rows: the whole warp on each, fixed xor tree
+            while (longm) {
+                const int i = __ffs(longm) - 1;
+                longm &= longm - 1;
+                const int b0 = __shfl_sync(0xffffffffu, a0, i), b1 = __shfl_sync(0xffffffffu, a1, i);
+                float a = 0.f;
+                for (int e = b0 + lane; e < b1; e += 32) a += svals[e];
+                a = warp_sum(a);
+                if (lane == 0) emit(r + i, a);
+            }
+            __syncwarp();
+            r += m;
+        }
+        if (r < rb) group_begin();
+    }
+    if (FUSED && p.det) {
+        // publish: one fence for everything this warp wrote (CSR row sums, dense-row partials), then one ticket per strip touched
+        const uint32_t hstage_u32 = svals_u32 + CSR_CH * 4;
+        const float *hstage = svals + CSR_CH;
+        __syncwarp();
+        if (p.rows && ra < rb)
+            for (int strip = ra / STRIP; strip <= (rb - 1) / STRIP; ++strip) warp_ticket(p, strip, lane, hstage_u32, hstage, hyb_tot);
+        if (hyb_on) {  // every distinct strip that owns a dense-row output channel
+            for (int j0 = 0; j0 < p.topX; ++j0) {
+                const int cj0 = __ldg(p.fri + j0);
+                if (cj0 < 0 || cj0 >= N) continue;
+                const int strip = cj0 / STRIP;
+                bool seen = false;
+                for (int j = 0; j < j0; ++j) {
+                    const int cj = __ldg(p.fri + j);
+                    seen |= (cj >= 0 && cj < N && cj / STRIP == strip);
                 }
-                __syncwarp();
-                cb = ce;
+                if (!seen) warp_ticket(p, strip, lane, hstage_u32, hstage, hyb_tot);
             }
         }
     }
@@ -646,22 +697,21 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
     unsigned char *sm = smem_raw + (sm_u32 - raw_u32);
     const int maxseg = p.maxseg;
     float *part = reinterpret_cast<float *>(sm + C::off_part(maxseg));
-    float *csr_acc = reinterpret_cast<float *>(sm + C::off_csr(maxseg));
-    int *srows = reinterpret_cast<int *>(sm + C::off_srows(maxseg));
     const uint32_t bar_u32 = sm_u32 + C::off_misc(maxseg);          // full[s] at +8s, empty[s] at +128+8s
     int *misc = reinterpret_cast<int *>(sm + C::off_misc(maxseg) + 256);
     float *hyb_tot = reinterpret_cast<float *>(sm + C::off_misc(maxseg) + 320);
     float *xs = reinterpret_cast<float *>(sm + C::off_x(maxseg));
     const uint32_t xs_u32 = sm_u32 + C::off_x(maxseg);
-    const uint32_t stage_u32 = sm_u32 + C::off_stage(maxseg, p.xfloats, p.has_csr != 0);
+    const uint32_t stage_u32 = sm_u32 + C::off_stage(maxseg, p.xfloats, p.has_stage != 0);
     const int nstage = p.nstage;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i16 = lane & 15, jsel = lane >> 4;  // column group (4 columns) and unit-of-the-pair of this lane
     const int N = p.N, R = p.R;
 
     // ---- this CTA's chunk of the flattened [strip][unit] space ----
     const int g0 = min((int)blockIdx.x * p.chunk, p.T);
-    const int g1 = (p.dbg & 2) ? g0 : min(g0 + p.chunk, p.T);
+    const int g1 = (DBG(p) & 2) ? g0 : min(g0 + p.chunk, p.T);
     const int len = g1 - g0;
     const int s0 = g0 / R;
     const int r0 = g0 - s0 * R;
@@ -697,25 +747,36 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
     };
     // cp.async mode: slot u of this thread lives at ring_u32 + ((u * ROWS_PER_UNIT + row) * NW*32 + tid) * 16 (consecutive threads are
     // contiguous: coalesced fills, conflict-free 128-bit reads).  Exactly one group is committed per position, valid or not,
-    // so "at most PF-1 groups pending" always means "the oldest position has landed".
+    // so "at most PF-1 groups pending" always means "the oldest position has landed".  A running global pointer follows the
+    // load cursor; it is re-derived only when the cursor enters a new segment.
     const uint32_t ring_u32 = stage_u32 + tid * 16;
-    auto cpa_issue = [&](int u) {
-        const int col0 = (s0 + ld.seg) * STRIP + 4 * (lane & 15);
-        const uint32_t dst = ring_u32 + u * (C::ROWS_PER_UNIT * NW * 32 * 16);
-        if (ld.o < len && col0 < N) {
-            const uint32_t *q = p.qw + (size_t)((ld.rr + (lane >> 4)) * C::ROWS_PER_UNIT) * N + col0;
+    constexpr uint32_t SLOT_STRIDE = C::ROWS_PER_UNIT * NW * 32 * 16;
+    const int warp2 = 2 * warp;
+    Cursor cl;
+    cl.seg = 0; cl.left = 0; cl.rr = 0;
+    const uint32_t *lptr = p.qw;
+    bool lvalid = false;
+    const size_t lstep = (size_t)SU * C::ROWS_PER_UNIT * N;  // words between consecutive positions of a warp
+    auto cl_setup = [&]() {
+        const int col0 = (s0 + cl.seg) * STRIP + 4 * i16;
+        lvalid = cl.seg < nseg && col0 < N;  // lanes past a ragged last strip fetch nothing (their LUT columns are zero)
+        if (lvalid) lptr = p.qw + (size_t)((cl.rr + jsel) * C::ROWS_PER_UNIT) * N + col0;
+    };
+    auto cpa_issue = [&](uint32_t dst) {
+        if (lvalid) {
 #pragma unroll
-            for (int r = 0; r < C::ROWS_PER_UNIT; ++r) cp_async16(dst + r * (NW * 32 * 16), q + (size_t)r * N);
-        } else {
-#pragma unroll
-            for (int r = 0; r < C::ROWS_PER_UNIT; ++r)
-                asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst + r * (NW * 32 * 16)), "r"(0u) : "memory");
+            for (int r = 0; r < C::ROWS_PER_UNIT; ++r) cp_async16(dst + r * (NW * 32 * 16), lptr + (size_t)r * N);
         }
         cp_async_commit();
-        ld.advance(SU, R);
+        if (cl.seg < nseg) {
+            lptr += lstep;
+            if (--cl.left == 0) {
+                cl.seek(cl.seg + 1, warp2, r0, R, len, nseg);
+                cl_setup();
+            }
+        }
     };
-    auto cpa_fetch = [&](Words<BITS> &w, int u) {
-        const uint32_t src = ring_u32 + u * (C::ROWS_PER_UNIT * NW * 32 * 16);
+    auto cpa_fetch = [&](Words<BITS> &w, uint32_t src) {
         w.a = lds_u4(src);
         if constexpr (BITS == 3) {
             w.b = lds_u4(src + NW * 32 * 16);
@@ -792,13 +853,15 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         }
         TRACE(9, lane == 0);
     } else if (warp == WARP_SPARSE) {
-        sparse_warp<BITS, FUSED>(p, sm, sm_u32, lane, nseg, s0, r0, csr_acc, srows, hyb_tot);
+        sparse_warp<BITS, FUSED>(p, sm, sm_u32, lane, hyb_tot + MAXSEG * MAX_TOPX_FUSED, nseg, s0);
         TRACE(10, lane == 0);
     } else {
         // ---- LDG mode: the first PF packed-word loads of every lane go out before anything else ----
         if (CPA_MODE) {
+            cl.seek(0, warp2, r0, R, len, nseg);
+            cl_setup();
 #pragma unroll
-            for (int u = 0; u < PF; ++u) cpa_issue(u);
+            for (int u = 0; u < PF; ++u) cpa_issue(ring_u32 + u * SLOT_STRIDE);
         } else if (LDG_MODE) {
 #pragma unroll
             for (int u = 0; u < PF; ++u) gload(ring[u]);
@@ -807,7 +870,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         {
             const int c = tid & (STRIP - 1), vg = tid >> 6;
             const int slot = ((c & 3) << 4) | (c >> 2);
-            for (int seg = 0; seg < ((p.dbg & 4) ? 0 : nseg); ++seg) {
+            for (int seg = 0; seg < ((DBG(p) & 4) ? 0 : nseg); ++seg) {
                 const int col = (s0 + seg) * STRIP + c;
                 const uint32_t dst = sm_u32 + seg * C::TAB + slot * 4;
 #pragma unroll
@@ -858,8 +921,6 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         TRACE(4, tid == 0);
     }
 
-    const int i16 = lane & 15, jsel = lane >> 4;
-
     if (warp < NW) {
         // =========================== consumer warps ===========================
         // Everything in this loop is addressed through 32-bit shared-window addresses (no generic pointers: those make
@@ -897,26 +958,31 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         UnitIt it;
         it.init(2 * warp, r0, R);
         if constexpr (CPA_MODE) {
-            // private cp.async ring: wait until slot u has landed, pull it into registers, refill the slot, then do the math
-            while (it.o < len) {
-#pragma unroll
-                for (int u = 0; u < PF; ++u) {
-                    if (it.o < len) {  // warp-uniform: len and o are even, a pair never straddles the end
-                        cp_async_wait_pending<PF - 1>();
-                        Words<BITS> cur;
-                        cpa_fetch(cur, u);
-                        if (it.seg != cur_seg) {
-                            if (cur_seg >= 0) deposit(cur_seg);
-                            cur_seg = it.seg;
-                            set_seg(cur_seg);
-                        }
-                        if (!(p.dbg & 1)) consume(cur, jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
-                        else acc[0] ^= cur.a.x;
-                        cpa_issue(u);  // the words are in registers (consumed above), the slot can be overwritten
-                        it.advance(SU, R);
-                    }
+            // private cp.async ring.  Outer loop: the segments (strips) this warp has positions in; inner loop: a fixed trip
+            // count of positions with nothing but running pointers: wait for the slot, pull it into registers, do the math,
+            // refill the slot PF positions ahead.
+            Cursor cc;
+            cc.seek(0, warp2, r0, R, len, nseg);
+            uint32_t slot = ring_u32;
+            const uint32_t slot_end = ring_u32 + PF * SLOT_STRIDE;
+            while (cc.seg < nseg) {
+                set_seg(cc.seg);
+                uint32_t xptr = xlane + (C::XU * 4) * (xdir ? cc.rr : cc.rr + cc.seg * R - r0);
+                for (int i = cc.left; i > 0; --i) {
+                    cp_async_wait_pending<PF - 1>();
+                    Words<BITS> cur;
+                    cpa_fetch(cur, slot);
+                    if (!(DBG(p) & 1)) consume(cur, jsel, lsb, segc, xptr, acc);
+                    else acc[0] ^= cur.a.x;
+                    cpa_issue(slot);  // the words are in registers (consumed above): the slot can be overwritten
+                    slot += SLOT_STRIDE;
+                    if (slot == slot_end) slot = ring_u32;
+                    xptr += SU * C::XU * 4;
                 }
+                deposit(cc.seg);
+                cc.seek(cc.seg + 1, warp2, r0, R, len, nseg);
             }
+            cur_seg = -1;  // everything already deposited
         } else if constexpr (LDG_MODE) {
             // register ring: consume slot u, immediately refill it with the pair PF positions ahead
             while (it.o < len) {
@@ -928,7 +994,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
                             cur_seg = it.seg;
                             set_seg(cur_seg);
                         }
-                        if (!(p.dbg & 1)) consume(ring[u], jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
+                        if (!(DBG(p) & 1)) consume(ring[u], jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
                         else acc[0] ^= ring[u].a.x;
                         gload(ring[u]);
                         it.advance(SU, R);
@@ -963,7 +1029,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
                         cur_seg = it.seg;
                         set_seg(cur_seg);
                     }
-                    if (!(p.dbg & 1)) consume(cur, jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
+                    if (!(DBG(p) & 1)) consume(cur, jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
                     else acc[0] ^= cur.a.x;
                 }
                 it.advance(SU, R);
@@ -988,7 +1054,6 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
             strip = s0 + seg;
 #pragma unroll
             for (int w = 0; w < NW; ++w) tot += part[(seg * NW + w) * STRIP + c];
-            tot += csr_acc[seg * STRIP + c];
         }
         if (!FUSED) {
             const int col = strip * STRIP + c;
@@ -996,13 +1061,15 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
             TRACE(11, tid == 0);
             return;
         }
+        if (!p.det) {  // fast fused mode: same red.add, into the zeroed scratch accumulator; conversion happens below
+            const int col = strip * STRIP + c;
+            if (active && col < N) atomicAdd(p.ws_acc + col, tot);
+        } else {
+        int expected = 1;
         if (active) {
-            const int first = (int)(((long long)strip * R) / p.chunk);
-            const int lastc = (int)((((long long)strip + 1) * R - 1) / p.chunk);
-            nd = lastc - first + 1;
-            slot = (int)blockIdx.x - first;
-            hyb = strip_has_hybrid(p, strip);
-            if (nd == 1 && !hyb) {  // this CTA owns the whole strip: store directly
+            expected = strip_contributors(p, strip, nd, hyb);
+            slot = (int)blockIdx.x - (int)(((long long)strip * R) / p.chunk);
+            if (expected == 1) {  // this CTA is the strip's only contributor: store directly
                 const int col = strip * STRIP + c;
                 if (col < N) {
                     if (p.bias) tot += p.bias[col];
@@ -1010,28 +1077,73 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
                     else reinterpret_cast<float *>(p.out)[col] = tot;
                 }
             } else {
-                p.ws_part[((size_t)strip * (p.maxc + 1) + slot) * STRIP + c] = tot;
-                __threadfence();  // each writer publishes its own partial before the ticket is taken
+                p.ws_part[((size_t)strip * p.maxc + slot) * STRIP + c] = tot;
             }
         }
         // ticket: 64 threads (2 warps) per segment; sync them with a named barrier per segment
-        const bool ticketed = active && !(nd == 1 && !hyb);
+        const bool ticketed = active && expected > 1;
         named_bar_sync(seg + 1, 64);
         if (c == 0) {
             int fin = 0;
             if (ticketed) {
-                __threadfence();
-                fin = (atomicAdd(p.ws_cnt + strip, 1) == nd + (hyb ? 1 : 0) - 1);
+                fin = (ticket_take(p.ws_cnt + strip) == expected - 1);
                 if (fin) p.ws_cnt[strip] = 0;
             }
             misc[seg] = fin;
         }
         named_bar_sync(seg + 1, 64);
         if (misc[seg]) {
-            __threadfence();
-            final_store(p, strip, c, nd, hyb);
+            float *ht = hyb_tot + seg * MAX_TOPX_FUSED;
+            if (hyb) {  // the first warp of this segment's pair stages and sums the dense-row partials, then both warps use them
+                const int cso = C::off_cstage(maxseg, p.xfloats);
+                if ((c >> 5) == 0) hybrid_totals(p, sm_u32 + cso + CSR_CH * 8, reinterpret_cast<const float *>(sm + cso + CSR_CH * 8), ht, lane);
+                named_bar_sync(seg + 1, 64);
+            }
+            final_store(p, strip, c, nd, hyb ? ht : nullptr);
         }
+        }  // det
         TRACE(11, tid == 0);
+    }
+    if (FUSED && !p.det) {
+        // One ticket per CTA; whoever draws the last one owns the finished accumulator: y = acc + bias (converted), acc = 0 for the
+        // next launch.  (All red.adds of this CTA precede the barrier; the acq_rel ticket publishes / acquires them.)
+        __syncthreads();
+        if (tid == 0) misc[8] = (ticket_take(p.ws_hyb_cnt) == (int)gridDim.x - 1);
+        __syncthreads();
+        if (misc[8]) {
+            if (tid == 0) *p.ws_hyb_cnt = 0;
+            // N % 4 == 0: float4 chunks, 4 independent chunks per thread per round so that the L2 round trips overlap
+            const float4 *acc4 = reinterpret_cast<const float4 *>(p.ws_acc);
+            const int n4 = N >> 2;
+            for (int c0 = tid; c0 < n4; c0 += 4 * THREADS) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c4 = c0 + u * THREADS;
+                    v[u] = c4 < n4 ? __ldcg(acc4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c4 = c0 + u * THREADS;
+                    if (c4 < n4) {
+                        reinterpret_cast<float4 *>(p.ws_acc)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias) + c4);
+                            v[u].x += b.x; v[u].y += b.y; v[u].z += b.z; v[u].w += b.w;
+                        }
+                        if (p.y_is_half) {
+                            __half2 lo = __floats2half2_rn(v[u].x, v[u].y), hi = __floats2half2_rn(v[u].z, v[u].w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                            pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                            reinterpret_cast<uint2 *>(p.out)[c4] = pk;
+                        } else {
+                            reinterpret_cast<float4 *>(p.out)[c4] = v[u];
+                        }
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -1081,6 +1193,7 @@ struct DevInfo {
 };
 DevInfo g_dev[64];
 int g_use_pdl = -1;
+int g_det = -1;  // fused mode: 1 = deterministic per-strip tickets, 0 = red.add + one global ticket (default; SQLLM_DETERMINISTIC=1 or sqllm_set_deterministic)
 int g_last_grid = 0;
 unsigned long long *g_trace = nullptr;
 size_t g_trace_stride = 0;
@@ -1131,10 +1244,13 @@ int get_tensor_map(const void *qweight, int rows, int cols, int box_rows, CUtens
 
 struct Plan {
     int R, strips, T, chunk, G, maxc, hc, hrows, smem, maxseg, nstage, x_direct, xfloats, tma2d, box_rows;
-    size_t ws_cnt_off, ws_hybcnt_off, ws_hyb_off, ws_part_off, ws_bytes;
+    size_t ws_cnt_off, ws_hybcnt_off, ws_hyb_off, ws_part_off, ws_csr_off, ws_acc_off, ws_bytes;
+    int csr_rpc, has_stage;
 };
 
-int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &pl) {
+int make_plan(int bits, int K, int N, int topX, bool has_csr_in, bool fused, Plan &pl) {
+    const bool has_csr = has_csr_in || topX > 0;  // from here on: "a staging buffer is needed"
+    pl.has_stage = has_csr ? 1 : 0;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail(SQLLM_ECUDA, "cudaGetDevice failed");
     if (dev < 0 || dev >= 64) return fail(SQLLM_EINVAL, "device ordinal %d out of range", dev);
@@ -1158,7 +1274,7 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &
     const long long T = (long long)pl.strips * pl.R;
     if (T > 0x3fffffff) return fail(SQLLM_EINVAL, "problem too large");
     pl.T = (int)T;
-    if (pl.strips > MAX_STRIPS) return fail(SQLLM_EINVAL, "out_features=%d exceeds the %d-strip workspace header", N, MAX_STRIPS);
+    if (pl.strips > MAX_STRIPS || (fused && N > MAX_N_FUSED)) return fail(SQLLM_EINVAL, "out_features=%d exceeds the workspace header (max %d)", N, MAX_N_FUSED);
 
     // Each kernel takes only CPS CTA slots per SM (default 2 of the 4 that fit): the rest of the SM is left to the NEXT
     // GEMV in the stream, which - launched with programmatic dependent launch - streams its weights into shared memory
@@ -1197,7 +1313,6 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &
     if (LDG_MODE) nstage = 0;  // weights go straight to registers
     const int smem = fixed + nstage * stage_bytes;
     if (smem > 227 * 1024) return fail(SQLLM_EINVAL, "in_features=%d needs %d B of shared memory (> 227 KB)", K, smem);
-    (void)fused;
     pl.smem = smem;
     pl.maxseg = maxseg;
     pl.nstage = nstage;
@@ -1208,11 +1323,17 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &
     pl.hc = 0;
     pl.hrows = 0;
     if (topX > 0) {
-        int hc = pl.G < K / 8 ? pl.G : K / 8;
+        // dense-row contributors: enough k-rows per CTA to amortise the latency, few enough partials (hc*topX floats) to fit
+        // the 2*CSR_CH-float staging buffer of the finisher
+        int hc = pl.G;
+        if (hc > K / 32) hc = K / 32;
+        if (hc > 2 * CSR_CH / topX) hc = 2 * CSR_CH / topX;
         if (hc < 1) hc = 1;
         pl.hrows = (K + hc - 1) / hc;
         pl.hc = (K + pl.hrows - 1) / pl.hrows;
     }
+    pl.csr_rpc = (N + pl.G - 1) / pl.G;
+    if (pl.csr_rpc < 1) pl.csr_rpc = 1;
     // Fixed header: [0,4) dense-row ticket, [256, 256+4*MAX_STRIPS) per-strip tickets.  Tickets must never
     // share bytes with data regions of ANY shape (the workspace is reused across layers of different sizes).
     size_t off = WS_HEADER;
@@ -1220,7 +1341,10 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr, bool fused, Plan &
     pl.ws_cnt_off = 256;
     pl.ws_hyb_off = off; off += (size_t)pl.hc * (topX > 0 ? topX : 0) * 4;
     off = (off + 255) & ~(size_t)255;
-    pl.ws_part_off = off; off += (size_t)pl.strips * (pl.maxc + 1) * STRIP * 4;
+    pl.ws_part_off = off; off += (size_t)pl.strips * pl.maxc * STRIP * 4;
+    off = (off + 255) & ~(size_t)255;
+    pl.ws_csr_off = off; off += (size_t)N * 4;
+    pl.ws_acc_off = WS_ACC_OFF;
     pl.ws_bytes = off;
     return SQLLM_OK;
 }
@@ -1272,6 +1396,8 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
     p.maxseg = pl.maxseg; p.nstage = pl.nstage; p.tma2d = pl.tma2d; p.x_direct = pl.x_direct; p.xfloats = pl.xfloats;
     p.hc = hyb ? pl.hc : 0; p.hrows = pl.hrows; p.maxc = pl.maxc;
     p.has_csr = a->rows ? 1 : 0;
+    p.has_stage = pl.has_stage;
+    p.csr_rpc = pl.csr_rpc;
     p.trace = g_trace;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SQLLM_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     if (g_trace) g_trace += g_trace_stride;
@@ -1294,6 +1420,7 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
 extern "C" {
 
 int sqllm_abi_version(void) { return SQLLM_ABI_VERSION; }
+void sqllm_set_deterministic(int on) { g_det = on ? 1 : 0; }
 
 // debug hook (not in the public header): successive launches write their timeline at buf, buf+stride, ...
 void sqllm_debug_set_trace(unsigned long long *buf, size_t stride_words) { g_trace = buf; g_trace_stride = stride_words; }
@@ -1346,6 +1473,7 @@ int sqllm_lutgemv_fused(const sqllm_lutgemv_args *a, const void *x, int x_is_hal
     if (rc) return rc;
     if (!x || !y) return fail(SQLLM_EINVAL, "x / y must not be null");
     if (reinterpret_cast<uintptr_t>(x) & 15) return fail(SQLLM_EINVAL, "x must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15)) return fail(SQLLM_EINVAL, "y and bias must be 16-byte aligned");
     const bool hyb = a->full_rows && a->topX > 0;
     if (hyb && a->topX > MAX_TOPX_FUSED) return fail(SQLLM_EINVAL, "fused path supports topX <= %d", MAX_TOPX_FUSED);
     Plan pl;
@@ -1360,6 +1488,10 @@ int sqllm_lutgemv_fused(const sqllm_lutgemv_args *a, const void *x, int x_is_hal
     p.ws_hyb_cnt = reinterpret_cast<int *>(ws + pl.ws_hybcnt_off);
     p.ws_hyb = reinterpret_cast<float *>(ws + pl.ws_hyb_off);
     p.ws_part = reinterpret_cast<float *>(ws + pl.ws_part_off);
+    p.ws_csr = reinterpret_cast<float *>(ws + pl.ws_csr_off);
+    p.ws_acc = reinterpret_cast<float *>(ws + pl.ws_acc_off);
+    if (g_det < 0) { const char *e = getenv("SQLLM_DETERMINISTIC"); g_det = (e && e[0] == '1') ? 1 : 0; }
+    p.det = g_det;
     p.x = x; p.x_is_half = x_is_half; p.out = y; p.y_is_half = y_is_half; p.bias = bias;
     return launch<true>(a, pl, p, static_cast<cudaStream_t>(stream));
 }

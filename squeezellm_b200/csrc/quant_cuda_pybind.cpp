@@ -245,5 +245,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("full_rows") = py::none(), py::arg("full_row_indices") = py::none());
     m.def("unpack_indices", &unpack_indices, "GPU unpack of the packed indices -> uint8 [in, out] (test hook)");
     m.def("abi_version", []() { return sqllm_abi_version(); });
+    m.def("set_deterministic", [](bool on) { sqllm_set_deterministic(on ? 1 : 0); },
+          "fused path: True = bit-reproducible fixed-order reduction, False (default) = red.add accumulation");
     m.def("sm_count", []() { return sqllm_device_sm_count(); });
 }

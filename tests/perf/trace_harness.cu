@@ -18,6 +18,8 @@ int main(int argc, char **argv) {
     setvbuf(stdout, NULL, _IONBF, 0);
     const int bits = argc > 1 ? atoi(argv[1]) : 4, K = argc > 2 ? atoi(argv[2]) : 4096, N = argc > 3 ? atoi(argv[3]) : 4096;
     const int chain = argc > 4 ? atoi(argv[4]) : 12, use_graph = argc > 5 ? atoi(argv[5]) : 1;
+    const int sparse = argc > 6 ? atoi(argv[6]) : 0;  // 1: CSR (0.45 %) + 10 zero dense rows, accumulate; 2: same, fused fp16
+
     const size_t qwords = (size_t)K / 32 * bits * N;
     const int copies = (size_t)K * N > (64u << 20) ? 3 : 40;
     uint32_t *q; float *lut, *x, *y; unsigned long long *trace;
@@ -27,6 +29,20 @@ int main(int argc, char **argv) {
     CK(cudaMalloc(&y, (size_t)N * 4 * chain)); CK(cudaMemset(y, 0, (size_t)N * 4 * chain));
     const size_t stride = 1024 * 32;
     CK(cudaMalloc(&trace, stride * 8 * chain)); CK(cudaMemset(trace, 0, stride * 8 * chain));
+    int *rows = nullptr, *cols = nullptr, *fri = nullptr; float *vals = nullptr, *fr = nullptr; void *ws = nullptr; size_t wsb = 0; void *xh = nullptr, *yh = nullptr;
+    if (sparse) {
+        const int per = (int)(0.0045 * K + 0.5); const size_t nnz = (size_t)per * N;
+        std::vector<int> hr(N + 1), hc(nnz);
+        for (int c = 0; c <= N; ++c) hr[c] = c * per;
+        for (size_t i = 0; i < nnz; ++i) hc[i] = (int)((i * 2654435761u) % K);
+        CK(cudaMalloc(&rows, (N + 1) * 4)); CK(cudaMemcpy(rows, hr.data(), (N + 1) * 4, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&cols, nnz * 4)); CK(cudaMemcpy(cols, hc.data(), nnz * 4, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&vals, nnz * 4)); CK(cudaMemset(vals, 0, nnz * 4));
+        CK(cudaMalloc(&fr, (size_t)K * 10 * 4)); CK(cudaMemset(fr, 0, (size_t)K * 10 * 4));
+        CK(cudaMalloc(&fri, 40)); CK(cudaMemset(fri, 0, 40));
+        wsb = 16u << 20; CK(cudaMalloc(&ws, wsb)); CK(cudaMemset(ws, 0, wsb));
+        CK(cudaMalloc(&xh, K * 2)); CK(cudaMemset(xh, 0, K * 2)); CK(cudaMalloc(&yh, (size_t)N * 2 * chain));
+    }
     cudaStream_t st; CK(cudaStreamCreate(&st));
     auto run_chain = [&](bool tr) {
         sqllm_debug_set_trace(tr ? trace : nullptr, tr ? stride : 0);
@@ -34,7 +50,8 @@ int main(int argc, char **argv) {
             sqllm_lutgemv_args a; memset(&a, 0, sizeof(a));
             a.bits = bits; a.in_features = K; a.out_features = N; a.batch = 1;
             a.qweight = (const int32_t *)(q + (size_t)(i % copies) * qwords); a.lookup_table = lut; a.vec = x; a.mul = y + (size_t)i * N;
-            int rc = sqllm_lutgemv(&a, st);
+            if (sparse) { a.rows = rows; a.cols = cols; a.vals = vals; a.full_rows = fr; a.full_row_indices = fri; a.topX = 10; }
+            int rc = sparse == 2 ? sqllm_lutgemv_fused(&a, xh, 1, (char *)yh + (size_t)i * N * 2, 1, nullptr, ws, wsb, st) : sqllm_lutgemv(&a, st);
             if (rc) { printf("error: %s\n", sqllm_last_error()); exit(1); }
         }
     };
@@ -63,13 +80,14 @@ int main(int argc, char **argv) {
     CK(cudaMemcpy(h.data(), trace, stride * 8 * chain, cudaMemcpyDeviceToHost));
     unsigned long long t00 = ~0ull;
     for (int c = 0; c < G; ++c) if (h[c * 32]) t00 = std::min(t00, h[c * 32]);
-    const char *names[12] = {"entry", "sync0", "pre-wait", "post-wait", "x-staged", "1st-full", "loop-end", "sync1", "tma-1st", "tma-last", "sparse", "exit"};
+    const char *names[16] = {"entry", "sync0", "pre-wait", "post-wait", "x-staged", "1st-full", "loop-end", "sync1", "tma-1st", "tma-last", "sparse", "exit", "smid", "sp-prewait", "sp-postwait", "sp-hybdone"};
     printf("%-4s", "k");
-    for (int s = 0; s < 12; ++s) printf(" %9s(min/max)", names[s]);
+    for (int s = 0; s < 16; ++s) if (s != 12) printf(" %9s(min/max)", names[s]);
     printf("\n");
     for (int i = 0; i < chain; ++i) {
         printf("%-4d", i);
-        for (int s = 0; s < 12; ++s) {
+        for (int s = 0; s < 16; ++s) {
+            if (s == 12) continue;
             unsigned long long mn = ~0ull, mx = 0;
             for (int c = 0; c < G; ++c) { unsigned long long v = h[(size_t)i * stride + c * 32 + s]; if (v) { mn = std::min(mn, v); mx = std::max(mx, v); } }
             if (mx) printf(" %8.2f/%8.2f", (mn - t00) / 1e3, (mx - t00) / 1e3); else printf(" %17s", "-");

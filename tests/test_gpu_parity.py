@@ -159,14 +159,20 @@ def test_fused_forward_vs_oracle(qc, shape, dtype):
     T = to_torch(L)
     xt = torch.from_numpy(x).cuda().reshape(-1).to(dtype)
     args = (xt, T["qweight"], T["lookup_table"], bits, T["bias"], T["rows"], T["cols"], T["vals"], T["full_rows"], T["full_row_indices"])
-    y1 = qc.lutgemv_fused(*args)
-    y2 = qc.lutgemv_fused(*args)
-    torch.cuda.synchronize()
+    y1 = qc.lutgemv_fused(*args)           # default: red.add accumulation (order may vary, like the reference's atomics)
+    qc.set_deterministic(True)             # fixed-order reduction: must be bit-reproducible
+    try:
+        d1 = qc.lutgemv_fused(*args)
+        d2 = qc.lutgemv_fused(*args)
+        torch.cuda.synchronize()
+    finally:
+        qc.set_deterministic(False)
     assert y1.dtype == dtype and y1.shape == (N,)
-    assert torch.equal(y1, y2), "fused path must be bit-deterministic"
+    assert torch.equal(d1, d2), "deterministic fused mode must be bit-reproducible"
     want = orc.forward_f64(L, x, mul_init=L["bias"][None, :])
-    e = rel_err(y1.float().cpu().numpy(), want)
-    assert e < (REL_TOL if dtype == torch.float16 else TIGHT_TOL), e  # fp16 output rounding is 2^-11 = 4.9e-4
+    for y in (y1, d1):
+        e = rel_err(y.float().cpu().numpy(), want)
+        assert e < (REL_TOL if dtype == torch.float16 else TIGHT_TOL), e  # fp16 output rounding is 2^-11 = 4.9e-4
 
 
 def test_module_forward_matches_reference_sequence(qc):
@@ -264,7 +270,7 @@ def test_current_stream_and_graph_capture(qc):
     x.copy_(x)  # no-op write; replay
     g.replay(); g.replay()
     torch.cuda.synchronize()
-    assert torch.equal(out, eager)
+    assert rel_err(out.float().cpu().numpy(), eager.float().cpu().numpy()) < REL_TOL  # default mode: last-bit differences allowed
 
 
 def test_errors_raise_runtimeerror(qc):

@@ -137,13 +137,11 @@ struct Cfg {
     static constexpr int PF = BITS == 4 ? SQLLM_PF4 : SQLLM_PF3;
     static constexpr int POS_BYTES = ROWS_PER_UNIT * 16;
     static constexpr int RING_BYTES = PF * NW * 32 * POS_BYTES;
-    // layout: [tables maxseg*TAB][part maxseg][csr_acc][srows][misc][x][csr stage][weight stages ...]
+    // layout: [tables maxseg*TAB][part maxseg][misc][x][csr stage][weight stages ...]
     __host__ __device__ static int off_part(int maxseg) { return maxseg * TAB; }
-    __host__ __device__ static int off_csr(int maxseg) { return off_part(maxseg) + maxseg * NW * STRIP * 4; }
-    __host__ __device__ static int off_srows(int maxseg) { return off_csr(maxseg) + MAXSEG * STRIP * 4; }
-    __host__ __device__ static int off_misc(int maxseg) { return off_srows(maxseg) + MAXSEG * SROWS_LD * 4; }
-    // misc: 2 x MAX_NSTAGE mbarriers (256 B) + 16 ints (64 B) + float[MAX_TOPX_FUSED]
-    __host__ __device__ static int off_x(int maxseg) { return off_misc(maxseg) + 256 + 64 + (MAXSEG + 1) * MAX_TOPX_FUSED * 4; }
+    __host__ __device__ static int off_misc(int maxseg) { return off_part(maxseg) + maxseg * NW * STRIP * 4; }
+    // misc: 2 x MAX_NSTAGE mbarriers (256 B) + 16 ints (64 B) + dense-row totals float[maxseg + 1][MAX_TOPX_FUSED]
+    __host__ __device__ static int off_x(int maxseg) { return off_misc(maxseg) + 256 + 64 + (maxseg + 1) * MAX_TOPX_FUSED * 4; }
     __host__ __device__ static int off_cstage(int maxseg, int xfloats) { return off_x(maxseg) + ((xfloats * 4 + 15) & ~15); }
     __host__ __device__ static int off_stage(int maxseg, int xfloats, bool csr) {  // csr: staging buffers present (CSR 8 KB + dense-row partials 8 KB)
         return (off_cstage(maxseg, xfloats) + (csr ? CSR_CH * 16 : 0) + 127) & ~127;
@@ -853,7 +851,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         }
         TRACE(9, lane == 0);
     } else if (warp == WARP_SPARSE) {
-        sparse_warp<BITS, FUSED>(p, sm, sm_u32, lane, hyb_tot + MAXSEG * MAX_TOPX_FUSED, nseg, s0);
+        sparse_warp<BITS, FUSED>(p, sm, sm_u32, lane, hyb_tot + maxseg * MAX_TOPX_FUSED, nseg, s0);
         TRACE(10, lane == 0);
     } else {
         // ---- LDG mode: the first PF packed-word loads of every lane go out before anything else ----
@@ -1287,7 +1285,11 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr_in, bool fused, Pla
         budget = (e2 ? atoi(e2) : 56) * 1024;
         if (budget < 16 * 1024 || budget > 227 * 1024) budget = 56 * 1024;
     }
-    const int G0 = d.sm * cps;
+    // The grid must be co-resident: a plan whose shared memory lets fewer than `cps` CTAs onto an SM would run a second wave.
+    // Plan for cps CTAs/SM, ask the occupancy calculator, and fall back to fewer CTAs per SM if it disagrees.
+    int use_cps = cps;
+replan:
+    const int G0 = d.sm * use_cps;
     // 2-D TMA boxes need every box inside one strip and one CTA range: units per box BU divides R and the chunk.
     const int BU = bits == 4 ? Cfg<4>::BU : Cfg<3>::BU;
     static int no_tma2d = -1;
@@ -1313,6 +1315,30 @@ int make_plan(int bits, int K, int N, int topX, bool has_csr_in, bool fused, Pla
     if (LDG_MODE) nstage = 0;  // weights go straight to registers
     const int smem = fixed + nstage * stage_bytes;
     if (smem > 227 * 1024) return fail(SQLLM_EINVAL, "in_features=%d needs %d B of shared memory (> 227 KB)", K, smem);
+    {
+        static std::mutex occ_mu;
+        static std::unordered_map<unsigned long long, int> occ_cache;
+        const unsigned long long key = ((unsigned long long)smem << 8) | (unsigned long long)((bits == 4 ? 2 : 0) | (fused ? 1 : 0));
+        int occ = -1;
+        {
+            std::lock_guard<std::mutex> lk(occ_mu);
+            auto it = occ_cache.find(key);
+            if (it != occ_cache.end()) occ = it->second;
+        }
+        if (occ < 0) {
+            const int threads = THREADS;
+            cudaError_t e;
+            if (bits == 4) e = fused ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lutgemv_kernel<4, true>, threads, smem)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lutgemv_kernel<4, false>, threads, smem);
+            else e = fused ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lutgemv_kernel<3, true>, threads, smem)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lutgemv_kernel<3, false>, threads, smem);
+            if (e != cudaSuccess) return fail(SQLLM_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+            std::lock_guard<std::mutex> lk(occ_mu);
+            occ_cache[key] = occ;
+        }
+        if (occ < 1) return fail(SQLLM_EINVAL, "kernel does not fit an SM (shared memory %d B)", smem);
+        if (occ < use_cps) { use_cps = occ; goto replan; }
+    }
     pl.smem = smem;
     pl.maxseg = maxseg;
     pl.nstage = nstage;

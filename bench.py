@@ -264,6 +264,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug only; the JSON says so)")
+    ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinearLUT (no q/k/v and gate/up sibling stacking)")
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload])
     if args.layers:
@@ -285,7 +286,16 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    layers, nbytes, nlaunch = build_model(cfg, dev, rank, world)
+    layers, nbytes, nmat = build_model(cfg, dev, rank, world)
+    nlaunch = nmat
+    if not args.no_fuse and world == 1:
+        # squeezellm_b200.fusion: siblings that read the same input run as one stacked launch (same packed words, same LUT rows)
+        from squeezellm_b200.fusion import SiblingGroup, LLAMA_SIBLINGS
+        for L in layers:
+            for names in LLAMA_SIBLINGS:
+                SiblingGroup([L[n] for n in names])
+                nlaunch -= len(names) - 1
+        torch.cuda.empty_cache()
     step = make_step(layers, world)
     x0 = torch.randn(cfg["hidden"], device=dev).half()
 
@@ -387,7 +397,8 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 accumulate (fp32 LUT x fp16->fp32 activations, fp16 outputs)", "data": "synthetic",
         "config": {"workload": args.workload, "batch": 1, "layers": cfg["layers"], "hidden": cfg["hidden"], "ffn": cfg["ffn"], "bits": cfg["bits"],
-                   "sparsity": cfg["sparsity"], "topX": cfg["topX"], "matvecs_per_step": nlaunch,
+                   "sparsity": cfg["sparsity"], "topX": cfg["topX"], "matvecs_per_step": nmat, "launches_per_step": nlaunch,
+                   "sibling_fusion": "q/k/v and gate/up stacked (squeezellm_b200.fusion)" if nlaunch != nmat else "off",
                    "scope": "QuantLinearLUT matvecs only; attention/norms/lm_head/KV cache excluded",
                    "l2": f"{nbytes_all / 1e9:.2f} GB of distinct weights per step >> 126 MB L2 (inputs larger than L2)",
                    "parallelism": "single GPU" if world == 1 else f"column-sharded x{world} + NCCL all-reduce per matvec",

@@ -74,6 +74,7 @@ constexpr int SU = 2 * NW;                // units per pipeline stage (one pair 
 constexpr int CSR_CH = 1024;              // CSR elements staged per chunk
 constexpr int SROWS_LD = 68;              // padded row-pointer slice per segment (65 used)
 constexpr int MAX_TOPX_FUSED = 128;
+constexpr int HYB_R = 11;                 // dense rows: k-rows per lane slot requested before the dependency wait
 constexpr int MAX_STRIPS = 16320;         // per-strip tickets in the workspace header (out_features <= 1,044,480)
 constexpr int MAX_N_FUSED = 262144;        // fused path: the scratch accumulator lives at a fixed place in the workspace
 constexpr size_t WS_ACC_OFF = 65536;       // [64 KB, 64 KB + 4*MAX_N_FUSED): fp32 accumulator (zero between launches)
@@ -111,6 +112,7 @@ struct Params {
     int *ws_hyb_cnt;  // [1]
     int has_csr;
     int has_stage;   // shared-memory staging buffer present (CSR and / or dense rows)
+    int csr_al16;    // cols / vals are 16-byte aligned: stage them with 16-byte cp.async
     int csr_rpc;     // CSR rows (output channels) handled per CTA: rows are spread evenly over all CTAs
     float *ws_csr;   // [N] CSR row sums (deterministic fused mode)
     float *ws_acc;   // [N] fp32 accumulator, zero between launches (fast fused mode)
@@ -179,6 +181,9 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_clip(uint32_t dst, const void *src, int src_bytes) {  // reads src_bytes (<= 16), zero-fills the rest
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -513,10 +518,9 @@ __device__ __forceinline__ void sparse_warp(const Params &p, unsigned char *sm, 
     const uint32_t scols_u32 = sm_u32 + cso, svals_u32 = scols_u32 + CSR_CH * 4;
 
     // ---------------- phase A: static data ----------------
-    constexpr int HYB_R = 11;
     float hfr[HYB_R];
     const bool hyb_on = p.full_rows && (int)blockIdx.x < p.hc;
-    const bool hyb_multi = hyb_on && p.topX <= 16;  // several k-rows per warp step: lane = (row slot, column j)
+    const bool hyb_multi = hyb_on && p.topX <= 32;  // 32/topX k-rows per warp step: lane = (row slot, column j)
     int kb = 0, ke = 0, nsl = 1, rs = 0, hj = lane;
     if (hyb_on) { kb = blockIdx.x * p.hrows; ke = min(p.K, kb + p.hrows); }
     if (hyb_multi) {
@@ -536,12 +540,25 @@ __device__ __forceinline__ void sparse_warp(const Params &p, unsigned char *sm, 
     auto group_begin = [&]() {  // row pointers one per lane, group size by ballot, then stage cols/vals
         rp = __ldg(p.rows + min(r + lane, rb));
         base = __shfl_sync(0xffffffffu, rp, 0);
-        const bool ok = lane <= min(31, rb - r) && rp - base <= CSR_CH;
+        const bool ok = lane <= min(31, rb - r) && rp - base <= CSR_CH - 4;
         m = __popc(__ballot_sync(0xffffffffu, ok)) - 1;  // rp is non-decreasing: the ok lanes are a prefix that includes lane 0
-        cnt = m > 0 ? __shfl_sync(0xffffffffu, rp, m) - base : 0;
-        for (int e = lane; e < cnt; e += 32) {
-            cp_async4(scols_u32 + 4 * e, p.cols + base + e);
-            cp_async4(svals_u32 + 4 * e, p.vals + base + e);
+        const int last = m > 0 ? __shfl_sync(0xffffffffu, rp, m) : base;
+        if (p.csr_al16 && m > 0) {
+            // 16-byte copies from the element-aligned-down start: up to 3 leading elements of earlier rows ride along (valid data,
+            // never summed); the last quad is clipped with the src-size operand, so nothing past `last` is read
+            base &= ~3;
+            cnt = last - base;
+            for (int e = 4 * lane; e < cnt; e += 128) {
+                const int nb = min(16, 4 * (cnt - e));
+                cp_async16_clip(scols_u32 + 4 * e, p.cols + base + e, nb);
+                cp_async16_clip(svals_u32 + 4 * e, p.vals + base + e, nb);
+            }
+        } else {
+            cnt = m > 0 ? last - base : 0;
+            for (int e = lane; e < cnt; e += 32) {
+                cp_async4(scols_u32 + 4 * e, p.cols + base + e);
+                cp_async4(svals_u32 + 4 * e, p.vals + base + e);
+            }
         }
         cp_async_commit();
     };
@@ -864,21 +881,31 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
 #pragma unroll
             for (int u = 0; u < PF; ++u) gload(ring[u]);
         }
-        // ---- consumers: stage the LUTs of this CTA's strips, transposed to [value][slot]; 2-way conflicts at worst ----
-        {
-            const int c = tid & (STRIP - 1), vg = tid >> 6;
-            const int slot = ((c & 3) << 4) | (c >> 2);
-            for (int seg = 0; seg < ((DBG(p) & 4) ? 0 : nseg); ++seg) {
-                const int col = (s0 + seg) * STRIP + c;
-                const uint32_t dst = sm_u32 + seg * C::TAB + slot * 4;
+        // ---- consumers: stage the LUTs of this CTA's strips, transposed to [value][slot].  One 128-bit load per (column, value
+        //      quad); a warp takes 32 columns whose slots fall in 32 different banks, so the four scalar stores are conflict-free.
+        //      (4-byte cp.async would cost 16 shared-memory wavefronts per warp instruction - measured, profiles/r01.) ----
+        constexpr int IPS = STRIP * C::L / 4;                 // (column, quad) items per strip: 256 (w4) / 128 (w3)
+        constexpr int LQ = MAXSEG * IPS / (NW * 32);          // items per thread at most
+        float4 lq[LQ];
 #pragma unroll
-                for (int v = vg; v < C::L; v += NW / 2) {
-                    if (col < N) cp_async4(dst + v * (STRIP * 4), p.lut + (size_t)col * C::L + v);
-                    else *reinterpret_cast<float *>(sm + seg * C::TAB + v * (STRIP * 4) + slot * 4) = 0.f;
-                }
-            }
+        for (int n = 0; n < LQ; ++n) {
+            const int it = tid + n * (NW * 32), seg = it / IPS, vw = (it % IPS) >> 5;
+            const int c = ((lane >> 1) << 2) | ((vw & 1) << 1) | (lane & 1), q = vw >> 1;
+            const int col = (s0 + seg) * STRIP + c;
+            lq[n] = (seg < nseg && col < N && !(DBG(p) & 4)) ? __ldg(reinterpret_cast<const float4 *>(p.lut + (size_t)col * C::L) + q)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         for (int e = tid; e < maxseg * NW * STRIP; e += NW * 32) part[e] = 0.f;
+#pragma unroll
+        for (int n = 0; n < LQ; ++n) {
+            const int it = tid + n * (NW * 32), seg = it / IPS, vw = (it % IPS) >> 5;
+            const int c = ((lane >> 1) << 2) | ((vw & 1) << 1) | (lane & 1), q = vw >> 1;
+            const int slot = ((c & 3) << 4) | (c >> 2);
+            if (seg < nseg) {
+                float *t = reinterpret_cast<float *>(sm + seg * C::TAB) + (4 * q) * STRIP + slot;
+                t[0] = lq[n].x; t[STRIP] = lq[n].y; t[2 * STRIP] = lq[n].z; t[3 * STRIP] = lq[n].w;
+            }
+        }
 
         TRACE(2, tid == 0);
         // Everything below reads data the previous kernel may have produced (x, mul, workspace).  One thread waits on the
@@ -900,13 +927,11 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
             const int src_f = ua * C::XU, dst_f = dst_unit * C::XU;
             if (p.x_is_half) {
                 const __half *xh = reinterpret_cast<const __half *>(p.x) + src_f;
-                for (int e = tid; e < nfl / 8; e += NW * 32) {
-                    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(xh) + e);
+                for (int e = tid; e < nfl / 4; e += NW * 32) {  // 4 halves in, one float4 out per thread: conflict-free stores
+                    const uint2 u = __ldg(reinterpret_cast<const uint2 *>(xh) + e);
                     const __half2 *h = reinterpret_cast<const __half2 *>(&u);
                     const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-                    const float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-                    reinterpret_cast<float4 *>(xs + dst_f)[2 * e] = make_float4(f0.x, f0.y, f1.x, f1.y);
-                    reinterpret_cast<float4 *>(xs + dst_f)[2 * e + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+                    reinterpret_cast<float4 *>(xs + dst_f)[e] = make_float4(f0.x, f0.y, f1.x, f1.y);
                 }
             } else {
                 const float *xf = reinterpret_cast<const float *>(p.x) + src_f;
@@ -1110,18 +1135,19 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         __syncthreads();
         if (misc[8]) {
             if (tid == 0) *p.ws_hyb_cnt = 0;
-            // N % 4 == 0: float4 chunks, 4 independent chunks per thread per round so that the L2 round trips overlap
+            // N % 4 == 0: float4 chunks, FB independent chunks per thread per round so that the L2 round trips overlap
+            constexpr int FB = 5;
             const float4 *acc4 = reinterpret_cast<const float4 *>(p.ws_acc);
             const int n4 = N >> 2;
-            for (int c0 = tid; c0 < n4; c0 += 4 * THREADS) {
-                float4 v[4];
+            for (int c0 = tid; c0 < n4; c0 += FB * THREADS) {
+                float4 v[FB];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < FB; ++u) {
                     const int c4 = c0 + u * THREADS;
                     v[u] = c4 < n4 ? __ldcg(acc4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < FB; ++u) {
                     const int c4 = c0 + u * THREADS;
                     if (c4 < n4) {
                         reinterpret_cast<float4 *>(p.ws_acc)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1191,7 +1217,12 @@ struct DevInfo {
 };
 DevInfo g_dev[64];
 int g_use_pdl = -1;
-int g_det = -1;  // fused mode: 1 = deterministic per-strip tickets, 0 = red.add + one global ticket (default; SQLLM_DETERMINISTIC=1 or sqllm_set_deterministic)
+int g_det = -1;
+int det_mode() {
+    if (g_det < 0) { const char *e = getenv("SQLLM_DETERMINISTIC"); g_det = (e && e[0] == '1') ? 1 : 0; }
+    return g_det;
+}
+// g_det - fused mode: 1 = deterministic per-strip tickets, 0 = red.add + one global ticket (default; SQLLM_DETERMINISTIC=1 or sqllm_set_deterministic)
 int g_last_grid = 0;
 unsigned long long *g_trace = nullptr;
 size_t g_trace_stride = 0;
@@ -1348,12 +1379,18 @@ replan:
     pl.maxc = (pl.R - 1) / chunk + 2;
     pl.hc = 0;
     pl.hrows = 0;
+    int hc_det = 0;  // workspace is sized for the deterministic mode whatever the current mode
     if (topX > 0) {
-        // dense-row contributors: enough k-rows per CTA to amortise the latency, few enough partials (hc*topX floats) to fit
-        // the 2*CSR_CH-float staging buffer of the finisher
+        // dense-row contributors: as few k-rows per CTA as the grid allows, down to what one warp requests before the dependency
+        // wait (HYB_R steps of 32/topX rows).  Deterministic mode also needs the partials (hc*topX floats) to fit the
+        // 2*CSR_CH-float staging buffer of the finisher.
+        const int rows_pre = HYB_R * (topX <= 32 ? 32 / topX : 1);
         int hc = pl.G;
-        if (hc > K / 32) hc = K / 32;
-        if (hc > 2 * CSR_CH / topX) hc = 2 * CSR_CH / topX;
+        if (hc > (K + rows_pre - 1) / rows_pre) hc = (K + rows_pre - 1) / rows_pre;
+        hc_det = hc;
+        if (hc_det > 2 * CSR_CH / topX) hc_det = 2 * CSR_CH / topX;
+        if (hc_det < 1) hc_det = 1;
+        if (fused && det_mode() == 1) hc = hc_det;
         if (hc < 1) hc = 1;
         pl.hrows = (K + hc - 1) / hc;
         pl.hc = (K + pl.hrows - 1) / pl.hrows;
@@ -1365,7 +1402,7 @@ replan:
     size_t off = WS_HEADER;
     pl.ws_hybcnt_off = 0;
     pl.ws_cnt_off = 256;
-    pl.ws_hyb_off = off; off += (size_t)pl.hc * (topX > 0 ? topX : 0) * 4;
+    pl.ws_hyb_off = off; off += (size_t)hc_det * (topX > 0 ? topX : 0) * 4;
     off = (off + 255) & ~(size_t)255;
     pl.ws_part_off = off; off += (size_t)pl.strips * pl.maxc * STRIP * 4;
     off = (off + 255) & ~(size_t)255;
@@ -1382,6 +1419,7 @@ int check_common(const sqllm_lutgemv_args *a) {
     if (a->out_features <= 0 || a->out_features % 4) return fail(SQLLM_EINVAL, "out_features=%d must be a positive multiple of 4", a->out_features);
     if (!a->qweight || !a->lookup_table) return fail(SQLLM_EINVAL, "qweight / lookup_table must not be null");
     if (reinterpret_cast<uintptr_t>(a->qweight) & 15) return fail(SQLLM_EINVAL, "qweight must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(a->lookup_table) & 15) return fail(SQLLM_EINVAL, "lookup_table must be 16-byte aligned");
     if (a->topX < 0) return fail(SQLLM_EINVAL, "topX < 0");
     if (a->full_rows && a->topX > 0 && !a->full_row_indices) return fail(SQLLM_EINVAL, "full_rows given without full_row_indices");
     return SQLLM_OK;
@@ -1424,6 +1462,7 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
     p.has_csr = a->rows ? 1 : 0;
     p.has_stage = pl.has_stage;
     p.csr_rpc = pl.csr_rpc;
+    p.csr_al16 = (a->rows && ((reinterpret_cast<uintptr_t>(a->cols) | reinterpret_cast<uintptr_t>(a->vals)) & 15) == 0) ? 1 : 0;
     p.trace = g_trace;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SQLLM_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     if (g_trace) g_trace += g_trace_stride;
@@ -1516,8 +1555,7 @@ int sqllm_lutgemv_fused(const sqllm_lutgemv_args *a, const void *x, int x_is_hal
     p.ws_part = reinterpret_cast<float *>(ws + pl.ws_part_off);
     p.ws_csr = reinterpret_cast<float *>(ws + pl.ws_csr_off);
     p.ws_acc = reinterpret_cast<float *>(ws + pl.ws_acc_off);
-    if (g_det < 0) { const char *e = getenv("SQLLM_DETERMINISTIC"); g_det = (e && e[0] == '1') ? 1 : 0; }
-    p.det = g_det;
+    p.det = det_mode();
     p.x = x; p.x_is_half = x_is_half; p.out = y; p.y_is_half = y_is_half; p.bias = bias;
     return launch<true>(a, pl, p, static_cast<cudaStream_t>(stream));
 }

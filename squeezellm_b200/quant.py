@@ -103,6 +103,7 @@ class QuantLinearLUT(nn.Module):
             self.register_buffer("full_rows", torch.zeros((infeatures, topX), dtype=torch.float32))
             self.register_buffer("full_row_indices", torch.zeros(topX, dtype=torch.int32))
         self.balanced = balanced
+        self._sibling_group = None  # (SiblingGroup, index) once fusion.fuse_siblings has stacked this layer with its siblings
 
     # ------------------------------------------------------------------------------------------
     def pack2(self, linear, lookup_table, include_sparse, num_nonzero_per_thread=-1):
@@ -144,6 +145,9 @@ class QuantLinearLUT(nn.Module):
         return self.rows, self.cols, self.vals, fr, fri
 
     def forward(self, x):
+        if self._sibling_group is not None:
+            group, index = self._sibling_group
+            return group.member_forward(index, x)
         dev = self.qweight.device
         if x.shape[-1] == x.numel():
             outshape = list(x.shape)

@@ -1,7 +1,9 @@
-run() { desc=$1; bin=$2; sh=$3; ch=$4; gr=$5; shift 5; out=$(env "$@" timeout 60 ./tests/perf/$bin 4 $sh $ch $gr 2>&1); echo "$desc [$*] $(echo "$out" | head -1)"; }
-for b in cpa8 cpa8_mb3; do for c in 2 3 4; do
-run "$b" th_$b "4096 4096" 16 1 SQLLM_CTAS_PER_SM=$c
-run "$b" th_$b "4096 11008" 16 1 SQLLM_CTAS_PER_SM=$c
-done; done
-run "dbg flags1" th_cpa8_dbg "4096 4096" 16 1 SQLLM_DEBUG_FLAGS=1
-run "dbg flags1" th_cpa8_dbg "4096 11008" 16 1 SQLLM_DEBUG_FLAGS=1
+run() { desc=$1; bin=$2; sh=$3; sp=$4; shift 4; out=$(env "$@" timeout 60 ./tests/perf/$bin 4 $sh 16 1 $sp 2>&1); echo "$desc [$sh sparse=$sp $*] $(echo "$out" | head -1)"; }
+for b in cpa8 cpa6 ldg6 ldg8 ldg4_mb4; do
+  for sp in 0 2; do
+    for sh in "4096 4096" "4096 11008" "11008 4096"; do
+      run "$b" th_$b "$sh" $sp SQLLM_CTAS_PER_SM=3
+    done
+  done
+done
+for b in ldg4_mb4 ldg6; do for sh in "4096 4096" "4096 11008"; do run "$b" th_$b "$sh" 2 SQLLM_CTAS_PER_SM=4; done; done

@@ -111,11 +111,12 @@ struct Params {
     float *ws_hyb;    // [hc][topX]
     int *ws_hyb_cnt;  // [1]
     int has_csr;
-    int has_stage;   // shared-memory staging buffer present (CSR and / or dense rows)
+    int has_stage;   // bytes of the shared-memory staging buffer: 0, CSR_CH*8 (CSR cols+vals) or CSR_CH*16 (+ dense-row partials, deterministic mode)
     int csr_al16;    // cols / vals are 16-byte aligned: stage them with 16-byte cp.async
     int csr_rpc;     // CSR rows (output channels) handled per CTA: rows are spread evenly over all CTAs
     float *ws_csr;   // [N] CSR row sums (deterministic fused mode)
     float *ws_acc;   // [N] fp32 accumulator, zero between launches (fast fused mode)
+    int smem_bytes;  // dynamic shared memory of this launch (the finalizer reuses it as staging)
     int det;         // fused mode: 1 = deterministic per-strip tickets, 0 = red.add into ws_acc + one global ticket per CTA
     int dbg;                    // debug: 1 = skip the gather/FMA math, 2 = no work at all, 4 = skip LUT staging (SQLLM_DEBUG_FLAGS)
     unsigned long long *trace;  // debug timeline (only written when built with -DSQLLM_TRACE and non-null)
@@ -145,10 +146,10 @@ struct Cfg {
     // misc: 2 x MAX_NSTAGE mbarriers (256 B) + 16 ints (64 B) + dense-row totals float[maxseg + 1][MAX_TOPX_FUSED]
     __host__ __device__ static int off_x(int maxseg) { return off_misc(maxseg) + 256 + 64 + (maxseg + 1) * MAX_TOPX_FUSED * 4; }
     __host__ __device__ static int off_cstage(int maxseg, int xfloats) { return off_x(maxseg) + ((xfloats * 4 + 15) & ~15); }
-    __host__ __device__ static int off_stage(int maxseg, int xfloats, bool csr) {  // csr: staging buffers present (CSR 8 KB + dense-row partials 8 KB)
-        return (off_cstage(maxseg, xfloats) + (csr ? CSR_CH * 16 : 0) + 127) & ~127;
+    __host__ __device__ static int off_stage(int maxseg, int xfloats, int csr) {  // csr: bytes of staging (CSR 8 KB [+ dense-row partials 8 KB])
+        return (off_cstage(maxseg, xfloats) + csr + 127) & ~127;
     }
-    __host__ __device__ static int total(int maxseg, int xfloats, bool csr, int nstage) {
+    __host__ __device__ static int total(int maxseg, int xfloats, int csr, int nstage) {
         return 4096 + off_stage(maxseg, xfloats, csr) + (CPA_MODE ? RING_BYTES : nstage * STAGE_BYTES);
     }
 };
@@ -717,7 +718,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
     float *hyb_tot = reinterpret_cast<float *>(sm + C::off_misc(maxseg) + 320);
     float *xs = reinterpret_cast<float *>(sm + C::off_x(maxseg));
     const uint32_t xs_u32 = sm_u32 + C::off_x(maxseg);
-    const uint32_t stage_u32 = sm_u32 + C::off_stage(maxseg, p.xfloats, p.has_stage != 0);
+    const uint32_t stage_u32 = sm_u32 + C::off_stage(maxseg, p.xfloats, p.has_stage);
     const int nstage = p.nstage;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -885,7 +886,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         //      quad); a warp takes 32 columns whose slots fall in 32 different banks, so the four scalar stores are conflict-free.
         //      (4-byte cp.async would cost 16 shared-memory wavefronts per warp instruction - measured, profiles/r01.) ----
         constexpr int IPS = STRIP * C::L / 4;                 // (column, quad) items per strip: 256 (w4) / 128 (w3)
-        constexpr int LQ = MAXSEG * IPS / (NW * 32);          // items per thread at most
+        constexpr int LQ = (MAXSEG * IPS + NW * 32 - 1) / (NW * 32);  // items per thread at most
         float4 lq[LQ];
 #pragma unroll
         for (int n = 0; n < LQ; ++n) {
@@ -1135,37 +1136,39 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         __syncthreads();
         if (misc[8]) {
             if (tid == 0) *p.ws_hyb_cnt = 0;
-            // N % 4 == 0: float4 chunks, FB independent chunks per thread per round so that the L2 round trips overlap
-            constexpr int FB = 5;
+            // The accumulator is pulled through shared memory (everything from the x slice on is free now) with 16-byte cp.async:
+            // all of a round's requests are in flight at once, so a round costs one L2 round trip however wide the layer is
+            // (register-staged loads needed one trip per ~5 KB per warp: 3 us of serial tail on a 22016-wide layer).
             const float4 *acc4 = reinterpret_cast<const float4 *>(p.ws_acc);
             const int n4 = N >> 2;
-            for (int c0 = tid; c0 < n4; c0 += FB * THREADS) {
-                float4 v[FB];
-#pragma unroll
-                for (int u = 0; u < FB; ++u) {
-                    const int c4 = c0 + u * THREADS;
-                    v[u] = c4 < n4 ? __ldcg(acc4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < FB; ++u) {
-                    const int c4 = c0 + u * THREADS;
-                    if (c4 < n4) {
-                        reinterpret_cast<float4 *>(p.ws_acc)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias) + c4);
-                            v[u].x += b.x; v[u].y += b.y; v[u].z += b.z; v[u].w += b.w;
-                        }
-                        if (p.y_is_half) {
-                            __half2 lo = __floats2half2_rn(v[u].x, v[u].y), hi = __floats2half2_rn(v[u].z, v[u].w);
-                            uint2 pk;
-                            pk.x = *reinterpret_cast<uint32_t *>(&lo);
-                            pk.y = *reinterpret_cast<uint32_t *>(&hi);
-                            reinterpret_cast<uint2 *>(p.out)[c4] = pk;
-                        } else {
-                            reinterpret_cast<float4 *>(p.out)[c4] = v[u];
-                        }
+            const int fin_off = C::off_x(maxseg);
+            const int cap4 = (p.smem_bytes - 4096 - fin_off) >> 4;
+            const float4 *st4 = reinterpret_cast<const float4 *>(sm + fin_off);
+            for (int b4 = 0; b4 < n4; b4 += cap4) {
+                const int m4 = min(cap4, n4 - b4);
+                for (int c = tid; c < m4; c += THREADS) cp_async16(sm_u32 + fin_off + 16 * c, acc4 + b4 + c);
+                cp_async_commit();
+                cp_async_wait_all();
+                __syncthreads();
+                for (int c = tid; c < m4; c += THREADS) {
+                    const int c4 = b4 + c;
+                    float4 v = st4[c];
+                    reinterpret_cast<float4 *>(p.ws_acc)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias) + c4);
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                    }
+                    if (p.y_is_half) {
+                        __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                        pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                        reinterpret_cast<uint2 *>(p.out)[c4] = pk;
+                    } else {
+                        reinterpret_cast<float4 *>(p.out)[c4] = v;
                     }
                 }
+                if (b4 + cap4 < n4) __syncthreads();  // the staging area is reused by the next round
             }
         }
     }
@@ -1279,7 +1282,8 @@ struct Plan {
 
 int make_plan(int bits, int K, int N, int topX, bool has_csr_in, bool fused, Plan &pl) {
     const bool has_csr = has_csr_in || topX > 0;  // from here on: "a staging buffer is needed"
-    pl.has_stage = has_csr ? 1 : 0;
+    // staging: CSR cols/vals chunks (8 KB); the deterministic fused mode also stages the dense-row partials there (8 KB more)
+    pl.has_stage = has_csr ? CSR_CH * 8 + ((fused && det_mode() == 1) ? CSR_CH * 8 : 0) : 0;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail(SQLLM_ECUDA, "cudaGetDevice failed");
     if (dev < 0 || dev >= 64) return fail(SQLLM_EINVAL, "device ordinal %d out of range", dev);
@@ -1337,7 +1341,7 @@ replan:
     const int xfl = direct ? K : chunk * XU;
     pl.x_direct = direct ? 1 : 0;
     const int stage_bytes = bits == 4 ? Cfg<4>::STAGE_BYTES : Cfg<3>::STAGE_BYTES;
-    const int fixed = bits == 4 ? Cfg<4>::total(maxseg, xfl, has_csr, 0) : Cfg<3>::total(maxseg, xfl, has_csr, 0);
+    const int fixed = bits == 4 ? Cfg<4>::total(maxseg, xfl, pl.has_stage, 0) : Cfg<3>::total(maxseg, xfl, pl.has_stage, 0);
     const int need = (chunk + SU - 1) / SU;
     int nstage = (budget - fixed) / stage_bytes;
     if (nstage > need) nstage = need;
@@ -1462,6 +1466,7 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
     p.has_csr = a->rows ? 1 : 0;
     p.has_stage = pl.has_stage;
     p.csr_rpc = pl.csr_rpc;
+    p.smem_bytes = pl.smem;
     p.csr_al16 = (a->rows && ((reinterpret_cast<uintptr_t>(a->cols) | reinterpret_cast<uintptr_t>(a->vals)) & 15) == 0) ? 1 : 0;
     p.trace = g_trace;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SQLLM_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }

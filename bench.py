@@ -233,6 +233,28 @@ def cpu_layer_sample(cfg, reps, seed=0):
     return times, fused_times, orc.threads()
 
 
+def leave(world):
+    """Multi-rank exit.  destroy_process_group() can block for ever while CUDA graphs that captured NCCL kernels are alive
+    (seen on 2 x B200: both ranks stuck after the JSON line was out), so ranks leave without tearing the communicator down."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
+def metric_name(workload):
+    if workload == "llama7b-w4-s45":
+        return "LLaMA-7B w4-s45 decode tokens/s at batch=1 (QuantLinear layers); per-layer HBM GB/s vs peak"
+    return f"{workload} decode tokens/s at batch=1 (QuantLinear layers)"
+
+
+def base_config(args, cfg):
+    return {"workload": args.workload, "batch": 1, "layers": cfg["layers"], "hidden": cfg["hidden"], "ffn": cfg["ffn"], "bits": cfg["bits"],
+            "sparsity": cfg["sparsity"], "topX": cfg["topX"], "matvecs_per_step": len(MATS) * cfg["layers"],
+            "scope": "QuantLinearLUT matvecs only; attention/norms/lm_head/KV cache excluded", "layers_overridden": bool(args.layers)}
+
+
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -244,10 +266,12 @@ def run_reference_arm(args, cfg):
     val = 1.0 / per_tok
     fused_val = 1.0 / (statistics.mean(fused[args.warmup:]) * cfg["layers"])
     sample = f"1 of {cfg['layers']} decoder layers (7 matvecs) per step, fp16 dequant + torch.matmul + CSR + dense rows; x{cfg['layers']} extrapolated"
-    out = {"metric": "decode tokens/s at batch=1 (QuantLinear layers)", "value": val, "unit": "tokens/s", "impl": "reference",
+    config = base_config(args, cfg)
+    config["note"] = "the reference has no CPU path; this arm is the CPU restatement north_star names (oracle/), all host threads"
+    out = {"metric": metric_name(args.workload), "value": val, "unit": "tokens/s", "impl": "reference",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_tok * 1e3, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f16 weights x f16 activations (torch CPU matmul)", "data": "synthetic",
-           "config": {"workload": args.workload, "batch": 1, "note": "reference has no CPU path; restatement named by north_star"},
+           "config": config,
            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
                             "fused_lookup_gemv_port_tokens_per_s": fused_val, "fused_port_threads": thr, "host_cpus": os.cpu_count()},
            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -284,6 +308,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one line
         dist.init_process_group("nccl", device_id=dev)
 
     layers, nbytes, nmat = build_model(cfg, dev, rank, world)
@@ -375,9 +401,7 @@ def main():
         nbytes_all = float(nbytes)
 
     if rank != 0:
-        if world > 1:
-            import torch.distributed as dist
-            dist.destroy_process_group()
+        leave(world)
         return
 
     ms_step = ms / args.steps
@@ -391,19 +415,15 @@ def main():
     except Exception:
         pass
     out = {
-        "metric": "LLaMA-7B w4-s45 decode tokens/s at batch=1 (QuantLinear layers); per-layer HBM GB/s vs peak" if args.workload == "llama7b-w4-s45"
-                  else f"{args.workload} decode tokens/s at batch=1 (QuantLinear layers)",
+        "metric": metric_name(args.workload),
         "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 accumulate (fp32 LUT x fp16->fp32 activations, fp16 outputs)", "data": "synthetic",
-        "config": {"workload": args.workload, "batch": 1, "layers": cfg["layers"], "hidden": cfg["hidden"], "ffn": cfg["ffn"], "bits": cfg["bits"],
-                   "sparsity": cfg["sparsity"], "topX": cfg["topX"], "matvecs_per_step": nmat, "launches_per_step": nlaunch,
+        "config": {**base_config(args, cfg), "launches_per_step": nlaunch,
                    "sibling_fusion": "q/k/v and gate/up stacked (squeezellm_b200.fusion)" if nlaunch != nmat else "off",
-                   "scope": "QuantLinearLUT matvecs only; attention/norms/lm_head/KV cache excluded",
                    "l2": f"{nbytes_all / 1e9:.2f} GB of distinct weights per step >> 126 MB L2 (inputs larger than L2)",
                    "parallelism": "single GPU" if world == 1 else f"column-sharded x{world} + NCCL all-reduce per matvec",
-                   "launch": "one CUDA-graph replay per step" if graphed else "eager launches (graph capture unavailable)",
-                   "layers_overridden": bool(args.layers)},
+                   "launch": "one CUDA-graph replay per step" if graphed else "eager launches (graph capture unavailable)"},
         "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": cfg["hidden"] * 2, "d2h_bytes_per_step": cfg["hidden"] * 2,
                 "api": "squeezellm_b200.runtime.GraphedDecodeStep over QuantLinearLUT.forward" if graphed else "QuantLinearLUT.forward eager"},
         "gpu_launches": nlaunch * args.steps,
@@ -421,9 +441,7 @@ def main():
                                "fused_lookup_gemv_port_tokens_per_s": 1.0 / (min(fused) * cfg["layers"]), "fused_port_threads": thr,
                                "host_cpus": os.cpu_count()}
     print(json.dumps(out), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+    leave(world)
 
 
 if __name__ == "__main__":

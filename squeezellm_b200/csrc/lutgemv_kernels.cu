@@ -51,7 +51,8 @@ namespace {
 #define SQLLM_LDG 2   // 2: per-thread private cp.async ring in shared memory (default); 1: LDG.128 register ring; 0: TMA producer warp + mbarrier ring
 #endif
 #ifndef SQLLM_MINB4
-#define SQLLM_MINB4 (SQLLM_LDG == 1 ? 3 : 4)   // resident CTAs per SM the register budget must allow
+#define SQLLM_MINB4 3   // resident CTAs per SM the register budget must allow (shared memory admits 3; at 4 the 56-register
+                        // cap makes the compiler rematerialise table addresses inside the loop: 6-13 % slower, profiles/r01)
 #endif
 #ifndef SQLLM_MINB3
 #define SQLLM_MINB3 3
@@ -116,7 +117,7 @@ struct Params {
     int csr_rpc;     // CSR rows (output channels) handled per CTA: rows are spread evenly over all CTAs
     float *ws_csr;   // [N] CSR row sums (deterministic fused mode)
     float *ws_acc;   // [N] fp32 accumulator, zero between launches (fast fused mode)
-    int smem_bytes;  // dynamic shared memory of this launch (the finalizer reuses it as staging)
+    int nfin;        // fast fused mode: CTAs (the last ones of the grid) that share the final conversion
     int det;         // fused mode: 1 = deterministic per-strip tickets, 0 = red.add into ws_acc + one global ticket per CTA
     int dbg;                    // debug: 1 = skip the gather/FMA math, 2 = no work at all, 4 = skip LUT staging (SQLLM_DEBUG_FLAGS)
     unsigned long long *trace;  // debug timeline (only written when built with -DSQLLM_TRACE and non-null)
@@ -1129,47 +1130,68 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         TRACE(11, tid == 0);
     }
     if (FUSED && !p.det) {
-        // One ticket per CTA; whoever draws the last one owns the finished accumulator: y = acc + bias (converted), acc = 0 for the
-        // next launch.  (All red.adds of this CTA precede the barrier; the acq_rel ticket publishes / acquires them.)
+        // Fast fused mode.  Every CTA announces "my red.adds are out" with one fire-and-forget red.release on a gpu-scope counter
+        // and leaves.  The last `nfin` CTAs of the grid (by index - they are dispatched last) stay, wait until the counter reaches
+        // the grid size, and each turns its 1/nfin slice of the accumulator into y (+ bias, converted) and re-zeroes it.  One CTA
+        // alone moves ~125 GB/s: 3.6 us for a 22016-wide layer (trace in profiles/r01); 16 of them need one L2 round trip.
+        // All CTAs of a launch are co-resident by construction (make_plan sizes the grid to the occupancy), so the wait cannot
+        // deadlock; the counter is reset by the last finisher for the next launch (kernel boundary orders it).
+        __syncthreads();  // all red.adds of this CTA issued
+        const int G = (int)gridDim.x, nfin = p.nfin;
+        const int fidx = (int)blockIdx.x - (G - nfin);
+        if (tid == 0) {
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.ws_hyb_cnt) : "memory");
+            if (fidx >= 0) {
+                int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.ws_hyb_cnt) : "memory");
+                    if (seen < G) __nanosleep(40);
+                } while (seen < G);
+            }
+        }
+        TRACE(8, tid == 0);  // (slots 8 / 9 double as "announced / all arrived" and "finalizer done" outside the TMA mode)
+        if (fidx < 0) return;
         __syncthreads();
-        if (tid == 0) misc[8] = (ticket_take(p.ws_hyb_cnt) == (int)gridDim.x - 1);
-        __syncthreads();
-        if (misc[8]) {
-            if (tid == 0) *p.ws_hyb_cnt = 0;
-            // The accumulator is pulled through shared memory (everything from the x slice on is free now) with 16-byte cp.async:
-            // all of a round's requests are in flight at once, so a round costs one L2 round trip however wide the layer is
-            // (register-staged loads needed one trip per ~5 KB per warp: 3 us of serial tail on a 22016-wide layer).
+        {
             const float4 *acc4 = reinterpret_cast<const float4 *>(p.ws_acc);
             const int n4 = N >> 2;
-            const int fin_off = C::off_x(maxseg);
-            const int cap4 = (p.smem_bytes - 4096 - fin_off) >> 4;
-            const float4 *st4 = reinterpret_cast<const float4 *>(sm + fin_off);
-            for (int b4 = 0; b4 < n4; b4 += cap4) {
-                const int m4 = min(cap4, n4 - b4);
-                for (int c = tid; c < m4; c += THREADS) cp_async16(sm_u32 + fin_off + 16 * c, acc4 + b4 + c);
-                cp_async_commit();
-                cp_async_wait_all();
-                __syncthreads();
-                for (int c = tid; c < m4; c += THREADS) {
-                    const int c4 = b4 + c;
-                    float4 v = st4[c];
-                    reinterpret_cast<float4 *>(p.ws_acc)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.bias) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias) + c4);
-                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                    }
-                    if (p.y_is_half) {
-                        __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
-                        uint2 pk;
-                        pk.x = *reinterpret_cast<uint32_t *>(&lo);
-                        pk.y = *reinterpret_cast<uint32_t *>(&hi);
-                        reinterpret_cast<uint2 *>(p.out)[c4] = pk;
-                    } else {
-                        reinterpret_cast<float4 *>(p.out)[c4] = v;
+            const int per = (n4 + nfin - 1) / nfin;
+            const int lo = min(n4, fidx * per), hi = min(n4, lo + per);
+            for (int c0 = lo + tid; c0 < hi; c0 += 4 * THREADS) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c4 = c0 + u * THREADS;
+                    v[u] = c4 < hi ? __ldcg(acc4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c4 = c0 + u * THREADS;
+                    if (c4 < hi) {
+                        reinterpret_cast<float4 *>(p.ws_acc)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias) + c4);
+                            v[u].x += bv.x; v[u].y += bv.y; v[u].z += bv.z; v[u].w += bv.w;
+                        }
+                        if (p.y_is_half) {
+                            __half2 lo2 = __floats2half2_rn(v[u].x, v[u].y), hi2 = __floats2half2_rn(v[u].z, v[u].w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t *>(&lo2);
+                            pk.y = *reinterpret_cast<uint32_t *>(&hi2);
+                            reinterpret_cast<uint2 *>(p.out)[c4] = pk;
+                        } else {
+                            reinterpret_cast<float4 *>(p.out)[c4] = v[u];
+                        }
                     }
                 }
-                if (b4 + cap4 < n4) __syncthreads();  // the staging area is reused by the next round
             }
+        }
+        TRACE(9, tid == 0);
+        __syncthreads();
+        if (tid == 0) {  // the finisher that completes the set puts both counters back to zero
+            int done;
+            asm volatile("atom.relaxed.gpu.global.add.s32 %0, [%1], 1;" : "=r"(done) : "l"(p.ws_hyb_cnt + 32) : "memory");
+            if (done == nfin - 1) { p.ws_hyb_cnt[0] = 0; p.ws_hyb_cnt[32] = 0; }
         }
     }
 }
@@ -1466,7 +1488,10 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
     p.has_csr = a->rows ? 1 : 0;
     p.has_stage = pl.has_stage;
     p.csr_rpc = pl.csr_rpc;
-    p.smem_bytes = pl.smem;
+    p.nfin = (a->out_features + 1023) / 1024;  // ~1024 columns per finishing CTA, at most 16 of them
+    if (p.nfin > 16) p.nfin = 16;
+    if (p.nfin > pl.G) p.nfin = pl.G;
+    if (p.nfin < 1) p.nfin = 1;
     p.csr_al16 = (a->rows && ((reinterpret_cast<uintptr_t>(a->cols) | reinterpret_cast<uintptr_t>(a->vals)) & 15) == 0) ? 1 : 0;
     p.trace = g_trace;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SQLLM_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }

@@ -57,9 +57,10 @@ const char *sqllm_last_error(void);
 int sqllm_device_sm_count(void);
 
 /* ---------------------------------------------------------------------------------------------
- * Workspace.  Used only by the *_fused entry point (deterministic cross-CTA reduction).  Must be
- * zero-filled once after allocation (cudaMemset); the library keeps it consistent afterwards.
- * One workspace must not be used by two streams concurrently.
+ * Workspace.  Used only by the *_fused entry point (cross-CTA accumulator, counters, deterministic-mode partials).
+ * Must be zero-filled once after allocation (cudaMemset); the library keeps it consistent afterwards.  One
+ * workspace serves layers of any shape, but must not be used by two streams concurrently.  The size returned
+ * does not depend on the summation mode.
  * ------------------------------------------------------------------------------------------- */
 size_t sqllm_workspace_bytes(int bits, int in_features, int out_features, int topX);
 
@@ -87,17 +88,20 @@ typedef struct sqllm_lutgemv_args {
 
 int sqllm_lutgemv(const sqllm_lutgemv_args *args, void *stream);
 
+/* Fused-path summation mode (process-wide).
+ *   0 (default; env SQLLM_DETERMINISTIC unset): contributions are added with red.add.f32 into a workspace accumulator, like the
+ *     reference's atomicAdd - results can differ in the last bits from run to run; the last CTAs of the grid convert it to y.
+ *   1: per-strip partials reduced in a fixed order by the last-arriving contributor - bit-reproducible, 1.3-2x slower on
+ *     layers with outliers. */
+void sqllm_set_deterministic(int on);
+
 /* Fused module path behind QuantLinearLUT.forward (squeezellm/quant.py:211-312), batch-1 decode:
  *   y[c] = bias[c] + LUT-GEMV + CSR + dense rows, written (not accumulated) as fp16 or fp32,
  * from an fp16 or fp32 x, in ONE launch: replaces torch.zeros (quant.py:218), x.float() (:223,267),
  * the 1-3 reference launches and y.to(dtype) (:311).  Summation order: see sqllm_set_deterministic.
- * x_is_half / y_is_half select the element type of x / y.  bias may be NULL. */
-/* Fused-path summation mode (process-wide).  0 (default, or env SQLLM_DETERMINISTIC unset): contributions are added with
- * red.add.f32 into a scratch accumulator, like the reference's atomicAdd - results can differ in the last bits from run to run.
- * 1: per-strip partials reduced in a fixed order by the last-arriving CTA - bit-reproducible, ~2x slower on sparse layers. */
-void sqllm_set_deterministic(int on);
-
-int sqllm_lutgemv_fused(const sqllm_lutgemv_args *args, /* vec/mul members ignored */
+ * x_is_half / y_is_half select the element type of x / y.  bias may be NULL.  x, y and bias must be 16-byte aligned;
+ * out_features <= 262144 and topX <= 128 on this path.  args->vec / args->mul / args->batch are ignored. */
+int sqllm_lutgemv_fused(const sqllm_lutgemv_args *args,
                         const void *x, int x_is_half, void *y, int y_is_half, const float *bias,
                         void *workspace, size_t workspace_bytes, void *stream);
 

@@ -382,11 +382,11 @@ template <> struct Words<4> { uint4 a; };
 template <> struct Words<3> { uint4 a, b, c; };
 
 __device__ __forceinline__ void consume(const Words<4> &g, const int jsel, const uint32_t lsb, const uint32_t segc,
-                                        const uint32_t xaddr, uint64_t (&acc)[4]) {
+                                        const uint32_t (&)[4], const uint32_t xaddr, uint64_t (&acc)[4]) {
     consume4(g.a, jsel, lsb, segc, xaddr, acc);
 }
-__device__ __forceinline__ void consume(const Words<3> &g, const int jsel, const uint32_t lsb, const uint32_t,
-                                        const uint32_t xaddr, uint64_t (&acc)[4]) {
+__device__ __forceinline__ void consume(const Words<3> &g, const int jsel, const uint32_t, const uint32_t,
+                                        const uint32_t (&lsv)[4], const uint32_t xaddr, uint64_t (&acc)[4]) {
     uint64_t xp[16];
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
@@ -398,7 +398,7 @@ __device__ __forceinline__ void consume(const Words<3> &g, const int jsel, const
     const uint32_t b[4] = {jsel ? g.b.y : g.b.x, jsel ? g.b.x : g.b.y, jsel ? g.b.w : g.b.z, jsel ? g.b.z : g.b.w};
     const uint32_t c[4] = {jsel ? g.c.y : g.c.x, jsel ? g.c.x : g.c.y, jsel ? g.c.w : g.c.z, jsel ? g.c.z : g.c.w};
 #pragma unroll
-    for (int t = 0; t < 4; ++t) consume3_col(a[t], b[t], c[t], lsb ^ (uint32_t)(t << 6), xp, acc[t]);
+    for (int t = 0; t < 4; ++t) consume3_col(a[t], b[t], c[t], lsv[t], xp, acc[t]);
 }
 __device__ __forceinline__ void gload_words(Words<4> &g, const uint32_t *q, size_t) { g.a = ldg_stream(q); }
 __device__ __forceinline__ void gload_words(Words<3> &g, const uint32_t *q, size_t N) {
@@ -952,6 +952,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         // the compiler rematerialise the window base through S2UR inside the loop when registers are tight).
         uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
         uint32_t lsb = 0u, segc = 0u;
+        uint32_t lsv[4] = {0u, 0u, 0u, 0u};
         int cur_seg = -1;
         const uint32_t part_u32 = sm_u32 + C::off_part(maxseg) + (warp * STRIP + 4 * i16) * 4;
         const uint32_t lane_slot = (uint32_t)((jsel << 6) | (i16 << 2));  // column 0 of this lane: slot ((0^jsel)<<4 | i16), x4 bytes
@@ -961,6 +962,15 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
             // 4-bit: byte 1 of the address comes from the nibble | segc (table 4 KB aligned); 3-bit: bits 8..10 are free (2 KB aligned)
             lsb = (BITS == 4 ? (tb & 0xFFFF0000u) : tb) | lane_slot;
             segc = ((tb >> 8) & 0xF0u) * 0x01010101u;
+            if constexpr (BITS == 3) {
+                // 3-bit: the four per-column slot addresses are pinned in registers for the whole segment.  Left to itself the
+                // compiler folds the `^ (t << 6)` into a second LOP3 per lookup (96 extra instructions per 128-weight position).
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    lsv[t] = lsb ^ (uint32_t)(t << 6);
+                    asm volatile("mov.u32 %0, %0;" : "+r"(lsv[t]));
+                }
+            }
         };
         auto deposit = [&](int seg) {
             float s[4];
@@ -997,7 +1007,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
                     cp_async_wait_pending<PF - 1>();
                     Words<BITS> cur;
                     cpa_fetch(cur, slot);
-                    if (!(DBG(p) & 1)) consume(cur, jsel, lsb, segc, xptr, acc);
+                    if (!(DBG(p) & 1)) consume(cur, jsel, lsb, segc, lsv, xptr, acc);
                     else acc[0] ^= cur.a.x;
                     cpa_issue(slot);  // the words are in registers (consumed above): the slot can be overwritten
                     slot += SLOT_STRIDE;
@@ -1019,7 +1029,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
                             cur_seg = it.seg;
                             set_seg(cur_seg);
                         }
-                        if (!(DBG(p) & 1)) consume(ring[u], jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
+                        if (!(DBG(p) & 1)) consume(ring[u], jsel, lsb, segc, lsv, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
                         else acc[0] ^= ring[u].a.x;
                         gload(ring[u]);
                         it.advance(SU, R);
@@ -1054,7 +1064,7 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
                         cur_seg = it.seg;
                         set_seg(cur_seg);
                     }
-                    if (!(DBG(p) & 1)) consume(cur, jsel, lsb, segc, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
+                    if (!(DBG(p) & 1)) consume(cur, jsel, lsb, segc, lsv, xlane + (C::XU * 4) * (xdir ? it.rr : it.o), acc);
                     else acc[0] ^= cur.a.x;
                 }
                 it.advance(SU, R);

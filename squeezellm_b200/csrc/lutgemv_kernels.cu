@@ -1498,8 +1498,16 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
     p.has_csr = a->rows ? 1 : 0;
     p.has_stage = pl.has_stage;
     p.csr_rpc = pl.csr_rpc;
-    p.nfin = (a->out_features + 1023) / 1024;  // ~1024 columns per finishing CTA, at most 16 of them
-    if (p.nfin > 16) p.nfin = 16;
+    {   // ~1024 columns per finishing CTA, at most 16 of them (SQLLM_NFIN_COLS / SQLLM_NFIN_MAX override, for experiments)
+        static int cols_per = 0, nmax = 0;
+        if (!cols_per) {
+            const char *e1 = getenv("SQLLM_NFIN_COLS"), *e2 = getenv("SQLLM_NFIN_MAX");
+            cols_per = e1 && atoi(e1) > 0 ? atoi(e1) : 1024;
+            nmax = e2 && atoi(e2) > 0 ? atoi(e2) : 16;
+        }
+        p.nfin = (a->out_features + cols_per - 1) / cols_per;
+        if (p.nfin > nmax) p.nfin = nmax;
+    }
     if (p.nfin > pl.G) p.nfin = pl.G;
     if (p.nfin < 1) p.nfin = 1;
     p.csr_al16 = (a->rows && ((reinterpret_cast<uintptr_t>(a->cols) | reinterpret_cast<uintptr_t>(a->vals)) & 15) == 0) ? 1 : 0;

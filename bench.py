@@ -130,33 +130,30 @@ def make_step(layers, world, hidden_dtype=torch.float16):
         return step
 
     import torch.distributed as dist
+    from squeezellm_b200.sharding import exchange_stacked
     rank = dist.get_rank()
-
-    def sharded(m, x, full):
-        """column shard -> its slice of a zero-padded full-length vector -> one all-reduce (north_star)."""
-        w = m.outfeatures
-        full.zero_()
-        full[rank * w:(rank + 1) * w] = m(x)
-        dist.all_reduce(full)
-        return full
-
     bufs = {}
 
-    def buf(name, n, dev):
+    def exchange(name, y, members):
+        """this rank's (stacked) column shard -> zero-padded full-length vectors -> ONE all-reduce (north_star)."""
+        w = y.shape[-1] // members
         if name not in bufs:
-            bufs[name] = torch.zeros(n, dtype=hidden_dtype, device=dev)
-        return bufs[name]
+            bufs[name] = torch.zeros((members, w * world), dtype=y.dtype, device=y.device)
+        return exchange_stacked(y, members, rank, world, out=bufs[name])
+
+    def stacked(L, names, x):
+        g = L[names[0]]._sibling_group
+        if g is not None:  # q/k/v (gate/up) shards stacked: one launch, one all-reduce for all members
+            return exchange(names[0], g[0].layer(x), len(names))
+        return [exchange(n, L[n](x), 1)[0] for n in names]
 
     def step(x):
         for L in layers:
-            for name in ("q_proj", "k_proj"):
-                sharded(L[name], x, buf(name, L[name].outfeatures * world, x.device))
-            v = sharded(L["v_proj"], x, buf("v", L["v_proj"].outfeatures * world, x.device))
-            o = sharded(L["o_proj"], v, buf("o", L["o_proj"].outfeatures * world, x.device))
-            g = sharded(L["gate_proj"], o, buf("g", L["gate_proj"].outfeatures * world, x.device))
-            sharded(L["up_proj"], o, buf("u", L["up_proj"].outfeatures * world, x.device))
-            x = sharded(L["down_proj"], g, buf("d", L["down_proj"].outfeatures * world, x.device)).clone()
-        return x
+            q, k, v = stacked(L, ("q_proj", "k_proj", "v_proj"), x)
+            o = exchange("o", L["o_proj"](v), 1)[0]
+            g, u = stacked(L, ("gate_proj", "up_proj"), o)
+            x = exchange("d", L["down_proj"](g), 1)[0]
+        return x.clone()
     return step
 
 
@@ -325,7 +322,7 @@ def main():
 
     layers, nbytes, nmat = build_model(cfg, dev, rank, world)
     nlaunch = nmat
-    if not args.no_fuse and world == 1:
+    if not args.no_fuse:
         # squeezellm_b200.fusion: siblings that read the same input run as one stacked launch (same packed words, same LUT rows)
         from squeezellm_b200.fusion import SiblingGroup, LLAMA_SIBLINGS
         for L in layers:
@@ -433,7 +430,7 @@ def main():
         "config": {**base_config(args, cfg), "launches_per_step": nlaunch,
                    "sibling_fusion": "q/k/v and gate/up stacked (squeezellm_b200.fusion)" if nlaunch != nmat else "off",
                    "l2": f"{nbytes_all / 1e9:.2f} GB of distinct weights per step >> 126 MB L2 (inputs larger than L2)",
-                   "parallelism": "single GPU" if world == 1 else f"column-sharded x{world} + NCCL all-reduce per matvec",
+                   "parallelism": "single GPU" if world == 1 else f"column-sharded x{world} + one NCCL all-reduce per launch ({nlaunch} per step)",
                    "launch": "one CUDA-graph replay per step" if graphed else "eager launches (graph capture unavailable)"},
         "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": cfg["hidden"] * 2, "d2h_bytes_per_step": cfg["hidden"] * 2,
                 "api": "squeezellm_b200.runtime.GraphedDecodeStep over QuantLinearLUT.forward" if graphed else "QuantLinearLUT.forward eager"},

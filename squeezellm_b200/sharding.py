@@ -84,3 +84,23 @@ class ShardedQuantLinearLUT(nn.Module):
         full[..., self.c0:self.c1] = y_local
         dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)  # sum of zero-padded slices
         return full
+
+
+def exchange_stacked(y_local, members, rank, world, out=None, group=None):
+    """Rebuild the full outputs of `members` sibling layers from one rank's stacked shard result.
+
+    y_local [..., members*w] is what this rank's stacked shard (fusion.SiblingGroup over its column shards, all of width
+    w = N/world) produced: member m's channels [rank*w, (rank+1)*w) at [m*w, (m+1)*w).  They are placed into a zeroed
+    [..., members, N] buffer and summed over ranks with ONE all-reduce (north_star's exchange, once per stacked launch
+    instead of once per member).  Returns that buffer; [..., m, :] is member m's full output vector.
+    `out` (optional, [..., members, N], same dtype/device) is reused instead of allocating."""
+    import torch.distributed as dist
+    lead = y_local.shape[:-1]
+    w = y_local.shape[-1] // members
+    if out is None:
+        out = torch.zeros(lead + (members, w * world), dtype=y_local.dtype, device=y_local.device)
+    else:
+        out.zero_()
+    out.view(lead + (members, world, w))[..., rank, :] = y_local.reshape(lead + (members, w))
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out

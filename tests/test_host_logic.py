@@ -125,3 +125,37 @@ def test_column_sharded_allreduce_world2_gloo():
     for rank, y, want in res:
         assert y.shape == (1, 136)
         assert rel_err(y, want) < TIGHT_TOL, f"rank {rank}"
+
+
+def _worker_stacked(rank, world, port, q):
+    import torch.distributed as dist
+    from squeezellm_b200.sharding import exchange_stacked
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, members = 24, 3
+        w = N // world
+        full = torch.arange(members * N, dtype=torch.float32).reshape(members, N) + 1.0   # member m's full output vector
+        y_local = torch.cat([full[m, rank * w:(rank + 1) * w] for m in range(members)])     # what the stacked shard computes
+        out = exchange_stacked(y_local, members, rank, world)
+        buf = torch.full((members, N), 7.0)                                                  # reused buffer must be re-zeroed
+        out2 = exchange_stacked(y_local, members, rank, world, out=buf)
+        q.put((rank, torch.equal(out, full), torch.equal(out2, full) and out2.data_ptr() == buf.data_ptr()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stacked_shard_exchange_world2_gloo():
+    """One all-reduce rebuilds the full outputs of all members of a stacked (q/k/v-style) column shard."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_stacked, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(a and b for _, a, b in res), res

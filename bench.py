@@ -114,7 +114,7 @@ def build_model(cfg, dev, rank, world, seed=0):
     return layers, nbytes, nlaunch
 
 
-def make_step(layers, world, hidden_dtype=torch.float16):
+def make_step(layers, world, peer=None):
     """x [hidden] -> x' [hidden]: the 7 matvecs per decoder layer in model order (see module docstring)."""
     if world == 1:
         def step(x):
@@ -133,6 +133,31 @@ def make_step(layers, world, hidden_dtype=torch.float16):
     from squeezellm_b200.sharding import exchange_stacked
     rank = dist.get_rank()
     bufs = {}
+    QKV, GU = ("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")
+
+    def group_layer(L, names):
+        g = L[names[0]]._sibling_group
+        return g[0].layer if g is not None else None
+
+    if peer is not None:
+        # the kernel's finishing CTAs store their slice into every rank's arena over NVLink and wait for the peers': no collective
+        def run(layer, x, slot, members):
+            return peer.forward(layer, x, slot, members, layer.outfeatures // members * world)
+
+        def stacked(L, names, x, slot):
+            layer = group_layer(L, names)
+            if layer is not None:
+                return run(layer, x, slot, len(names))
+            return [run(L[n], x, slot + n, 1)[0] for n in names]
+
+        def step(x):
+            for L in layers:
+                q, k, v = stacked(L, QKV, x, "qkv")
+                o = run(L["o_proj"], v, "o", 1)[0]
+                g, u = stacked(L, GU, o, "gu")
+                x = run(L["down_proj"], g, "d", 1)[0]
+            return x.clone()
+        return step
 
     def exchange(name, y, members):
         """this rank's (stacked) column shard -> zero-padded full-length vectors -> ONE all-reduce (north_star)."""
@@ -142,16 +167,16 @@ def make_step(layers, world, hidden_dtype=torch.float16):
         return exchange_stacked(y, members, rank, world, out=bufs[name])
 
     def stacked(L, names, x):
-        g = L[names[0]]._sibling_group
-        if g is not None:  # q/k/v (gate/up) shards stacked: one launch, one all-reduce for all members
-            return exchange(names[0], g[0].layer(x), len(names))
+        layer = group_layer(L, names)
+        if layer is not None:  # q/k/v (gate/up) shards stacked: one launch, one all-reduce for all members
+            return exchange(names[0], layer(x), len(names))
         return [exchange(n, L[n](x), 1)[0] for n in names]
 
     def step(x):
         for L in layers:
-            q, k, v = stacked(L, ("q_proj", "k_proj", "v_proj"), x)
+            q, k, v = stacked(L, QKV, x)
             o = exchange("o", L["o_proj"](v), 1)[0]
-            g, u = stacked(L, ("gate_proj", "up_proj"), o)
+            g, u = stacked(L, GU, o)
             x = exchange("d", L["down_proj"](g), 1)[0]
         return x.clone()
     return step
@@ -285,6 +310,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug only; the JSON says so)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: how column shards are reassembled - p2p: stores into every rank's symmetric arena from inside the GEMV "
+                         "kernel (falls back to nccl if symmetric memory is unavailable or the self-check fails); nccl: one all-reduce per launch")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinearLUT (no q/k/v and gate/up sibling stacking)")
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload])
@@ -330,7 +358,34 @@ def main():
                 SiblingGroup([L[n] for n in names])
                 nlaunch -= len(names) - 1
         torch.cuda.empty_cache()
-    step = make_step(layers, world)
+    exchange_used = "none"
+    if world > 1:
+        import torch.distributed as dist
+        step_nccl = make_step(layers, world)
+        step, exchange_used = step_nccl, "nccl all-reduce per launch"
+        if args.exchange == "p2p":
+            why, ok, step_p2p = None, 0.0, None
+            try:
+                from squeezellm_b200.sharding import PeerExchange
+                peer = PeerExchange(rank, world, dev)
+                step_p2p = make_step(layers, world, peer)
+                xs = torch.randn(cfg["hidden"], device=dev, generator=torch.Generator(device=dev).manual_seed(7)).half()
+                a, b = step_p2p(xs).float(), step_nccl(xs).float()
+                torch.cuda.synchronize()
+                good = (not peer.error()) and bool(torch.isfinite(a).all()) and bool((a - b).abs().max() <= 2e-2 * b.abs().max().clamp_min(1e-3))
+                ok = 1.0 if good else 0.0
+                if not good:
+                    why = "self-check against the NCCL path failed"
+            except Exception as e:  # noqa: BLE001 - symmetric memory unavailable: keep the NCCL path
+                why = f"{type(e).__name__}: {e}"
+            vote = torch.tensor([ok], device=dev)
+            dist.all_reduce(vote, op=dist.ReduceOp.MIN)  # every rank takes the same decision
+            if vote.item() == 1.0:
+                step, exchange_used = step_p2p, "in-kernel stores to every rank's symmetric arena over NVLink (no collective)"
+            elif why or rank == 0:
+                print(f"[bench] rank {rank}: p2p exchange not used ({why or 'another rank declined'}); falling back to NCCL", file=sys.stderr)
+    else:
+        step = make_step(layers, world)
     x0 = torch.randn(cfg["hidden"], device=dev).half()
 
     def barrier():
@@ -430,7 +485,7 @@ def main():
         "config": {**base_config(args, cfg), "launches_per_step": nlaunch,
                    "sibling_fusion": "q/k/v and gate/up stacked (squeezellm_b200.fusion)" if nlaunch != nmat else "off",
                    "l2": f"{nbytes_all / 1e9:.2f} GB of distinct weights per step >> 126 MB L2 (inputs larger than L2)",
-                   "parallelism": "single GPU" if world == 1 else f"column-sharded x{world} + one NCCL all-reduce per launch ({nlaunch} per step)",
+                   "parallelism": "single GPU" if world == 1 else f"column-sharded x{world}, {nlaunch} launches per step", "exchange": exchange_used,
                    "launch": "one CUDA-graph replay per step" if graphed else "eager launches (graph capture unavailable)"},
         "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": cfg["hidden"] * 2, "d2h_bytes_per_step": cfg["hidden"] * 2,
                 "api": "squeezellm_b200.runtime.GraphedDecodeStep over QuantLinearLUT.forward" if graphed else "QuantLinearLUT.forward eager"},

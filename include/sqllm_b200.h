@@ -105,6 +105,31 @@ int sqllm_lutgemv_fused(const sqllm_lutgemv_args *args,
                         const void *x, int x_is_half, void *y, int y_is_half, const float *bias,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* Fused forward of a COLUMN SHARD with the exchange built in (multi-GPU; the reference has none - north_star's
+ * "column-shard each QuantLinear + all-reduce on the output vector", done by the kernel instead of a separate collective).
+ * Every rank calls this with its shard (args->out_features = members * w columns: `members` sibling layers stacked, each
+ * contributing this rank's w columns [rank*w, (rank+1)*w) of its out_features_full).  The CTAs that finish the GEMV store
+ * their slice of y straight into EVERY rank's arena over NVLink peer memory - member m, column rank*w + j goes to element
+ * [m][rank*w + j] of a [members][out_features_full] vector at out_offset - publish with a system-scope release on a
+ * counter in each arena, and wait (bounded: 2 s, then *error_offset = 1) until all ranks' finishers have published on the
+ * local one.  When the call's grid completes, the local vector is whole: the next stream-ordered consumer may read it.
+ *   peer_base    device array [world] of the arenas' base addresses (e.g. torch symmetric memory's buffer_ptrs_dev)
+ *   *_offset     byte offsets inside every arena: the destination vector, a u64 arrival counter (zero-initialised, only
+ *                ever incremented), this rank's u64 expected-arrivals word (zero-initialised, local use), a u32 error word.
+ * All ranks must issue the same sequence of exchange calls; consecutive calls must not target the same destination
+ * (a fast rank may deliver call k+1 while a slow one still reads the result of call k).  Default summation mode only. */
+typedef struct sqllm_exchange {
+    int world, rank;
+    int members;
+    int out_features_full;
+    const uint64_t *peer_base;
+    size_t out_offset, flag_offset, state_offset, error_offset;
+} sqllm_exchange;
+
+int sqllm_lutgemv_fused_exchange(const sqllm_lutgemv_args *args,
+                                 const void *x, int x_is_half, int y_is_half, const float *bias,
+                                 void *workspace, size_t workspace_bytes, const sqllm_exchange *xchg, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * The reference's 12 launchers, one C entry point each.
  * ------------------------------------------------------------------------------------------- */

@@ -117,6 +117,10 @@ struct Params {
     int csr_rpc;     // CSR rows (output channels) handled per CTA: rows are spread evenly over all CTAs
     float *ws_csr;   // [N] CSR row sums (deterministic fused mode)
     float *ws_acc;   // [N] fp32 accumulator, zero between launches (fast fused mode)
+    // optional exchange (column-sharded layers): finishers store their slice into every rank's arena over NVLink
+    int xw_world, xw_rank, xw_members, xw_nfull;   // xw_world == 0: no exchange
+    const unsigned long long *xw_base;             // device array [world]: base address of every rank's symmetric arena
+    unsigned long long xw_out_off, xw_flag_off, xw_state_off, xw_err_off;
     int nfin;        // fast fused mode: CTAs (the last ones of the grid) that share the final conversion
     int det;         // fused mode: 1 = deterministic per-strip tickets, 0 = red.add into ws_acc + one global ticket per CTA
     int dbg;                    // debug: 1 = skip the gather/FMA math, 2 = no work at all, 4 = skip LUT staging (SQLLM_DEBUG_FLAGS)
@@ -1183,14 +1187,25 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
                             const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias) + c4);
                             v[u].x += bv.x; v[u].y += bv.y; v[u].z += bv.z; v[u].w += bv.w;
                         }
+                        uint2 pk = make_uint2(0u, 0u);
                         if (p.y_is_half) {
                             __half2 lo2 = __floats2half2_rn(v[u].x, v[u].y), hi2 = __floats2half2_rn(v[u].z, v[u].w);
-                            uint2 pk;
                             pk.x = *reinterpret_cast<uint32_t *>(&lo2);
                             pk.y = *reinterpret_cast<uint32_t *>(&hi2);
-                            reinterpret_cast<uint2 *>(p.out)[c4] = pk;
+                        }
+                        if (p.xw_world == 0) {
+                            if (p.y_is_half) reinterpret_cast<uint2 *>(p.out)[c4] = pk;
+                            else reinterpret_cast<float4 *>(p.out)[c4] = v[u];
                         } else {
-                            reinterpret_cast<float4 *>(p.out)[c4] = v[u];
+                            // local column 4*c4 of the stacked shard = column j of member m; it lands at [m][rank*w + j] of the
+                            // [members][n_full] vector in EVERY rank's arena (w % 4 == 0: a quad never straddles members)
+                            const int w = N / p.xw_members, col = 4 * c4, m = col / w, j = col - m * w;
+                            const unsigned long long e = (unsigned long long)m * p.xw_nfull + (unsigned long long)p.xw_rank * w + j;
+                            for (int pr = 0; pr < p.xw_world; ++pr) {
+                                unsigned char *dst = reinterpret_cast<unsigned char *>(__ldg(p.xw_base + pr) + p.xw_out_off);
+                                if (p.y_is_half) *reinterpret_cast<uint2 *>(dst + 2 * e) = pk;
+                                else *reinterpret_cast<float4 *>(dst + 4 * e) = v[u];
+                            }
                         }
                     }
                 }
@@ -1198,10 +1213,37 @@ __global__ void __launch_bounds__(THREADS, BITS == 4 ? SQLLM_MINB4 : SQLLM_MINB3
         }
         TRACE(9, tid == 0);
         __syncthreads();
-        if (tid == 0) {  // the finisher that completes the set puts both counters back to zero
+        if (tid == 0) {
+            unsigned long long target = 0ull;
+            if (p.xw_world) {
+                // publish this finisher's stores on every rank (system-scope release), then wait until every finisher of every
+                // rank has published on ours: when this grid completes, the local vector is whole.  Counters only grow
+                // (expected arrivals so far live next to the flag), so nothing is ever reset across ranks.  The wait is bounded:
+                // a rank that never shows up sets the error word instead of hanging the GPU.
+                const unsigned long long self = __ldg(p.xw_base + p.xw_rank);
+                target = *reinterpret_cast<volatile unsigned long long *>(self + p.xw_state_off) + (unsigned long long)p.xw_world * nfin;
+                __threadfence_system();
+                for (int pr = 0; pr < p.xw_world; ++pr)
+                    atomicAdd_system(reinterpret_cast<unsigned long long *>(__ldg(p.xw_base + pr) + p.xw_flag_off), 1ull);
+                unsigned long long seen, t0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                const bool broken = *reinterpret_cast<volatile unsigned int *>(self + p.xw_err_off) != 0u;  // an earlier wait gave up: do not wait again
+                if (!broken) do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(self + p.xw_flag_off) : "memory");
+                    if (seen >= target) break;
+                    __nanosleep(100);
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 2000000000ull) { *reinterpret_cast<volatile unsigned int *>(self + p.xw_err_off) = 1u; break; }
+                } while (true);
+            }
+            // the finisher that completes the set puts both counters back to zero (and advances the expected arrivals)
             int done;
             asm volatile("atom.relaxed.gpu.global.add.s32 %0, [%1], 1;" : "=r"(done) : "l"(p.ws_hyb_cnt + 32) : "memory");
-            if (done == nfin - 1) { p.ws_hyb_cnt[0] = 0; p.ws_hyb_cnt[32] = 0; }
+            if (done == nfin - 1) {
+                p.ws_hyb_cnt[0] = 0;
+                p.ws_hyb_cnt[32] = 0;
+                if (p.xw_world) *reinterpret_cast<volatile unsigned long long *>(__ldg(p.xw_base + p.xw_rank) + p.xw_state_off) = target;
+            }
         }
     }
 }
@@ -1605,6 +1647,46 @@ int sqllm_lutgemv_fused(const sqllm_lutgemv_args *a, const void *x, int x_is_hal
     p.ws_acc = reinterpret_cast<float *>(ws + pl.ws_acc_off);
     p.det = det_mode();
     p.x = x; p.x_is_half = x_is_half; p.out = y; p.y_is_half = y_is_half; p.bias = bias;
+    return launch<true>(a, pl, p, static_cast<cudaStream_t>(stream));
+}
+
+int sqllm_lutgemv_fused_exchange(const sqllm_lutgemv_args *a, const void *x, int x_is_half, int y_is_half, const float *bias,
+                                 void *workspace, size_t workspace_bytes, const sqllm_exchange *xc, void *stream) {
+    int rc = check_common(a);
+    if (rc) return rc;
+    if (!x || !xc) return fail(SQLLM_EINVAL, "x / exchange descriptor must not be null");
+    if (reinterpret_cast<uintptr_t>(x) & 15) return fail(SQLLM_EINVAL, "x must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(bias) & 15) return fail(SQLLM_EINVAL, "bias must be 16-byte aligned");
+    if (det_mode() == 1) return fail(SQLLM_EINVAL, "the exchange path needs the default (non-deterministic) fused mode");
+    if (xc->world < 1 || xc->world > 64 || xc->rank < 0 || xc->rank >= xc->world) return fail(SQLLM_EINVAL, "bad world / rank (%d / %d)", xc->world, xc->rank);
+    if (xc->members < 1 || a->out_features % xc->members) return fail(SQLLM_EINVAL, "out_features=%d is not %d equal members", a->out_features, xc->members);
+    const int w = a->out_features / xc->members;
+    if (w % 4) return fail(SQLLM_EINVAL, "shard width %d must be a multiple of 4", w);
+    if (xc->out_features_full < xc->world * w) return fail(SQLLM_EINVAL, "out_features_full=%d < world * shard width = %d", xc->out_features_full, xc->world * w);
+    if (!xc->peer_base) return fail(SQLLM_EINVAL, "peer_base must not be null");
+    if ((xc->out_offset & 15) || (xc->flag_offset & 7) || (xc->state_offset & 7) || (xc->error_offset & 3)) return fail(SQLLM_EINVAL, "misaligned arena offsets");
+    if ((xc->out_features_full * (y_is_half ? 2 : 4)) % 16 || (w * (y_is_half ? 2 : 4)) % 8) return fail(SQLLM_EINVAL, "vector sizes must keep 8/16-byte store alignment");
+    const bool hyb = a->full_rows && a->topX > 0;
+    if (hyb && a->topX > MAX_TOPX_FUSED) return fail(SQLLM_EINVAL, "fused path supports topX <= %d", MAX_TOPX_FUSED);
+    Plan pl;
+    rc = make_plan(a->bits, a->in_features, a->out_features, hyb ? a->topX : 0, a->rows != nullptr, true, pl);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < pl.ws_bytes)
+        return fail(SQLLM_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.ws_bytes, workspace_bytes);
+    Params p;
+    memset(&p, 0, sizeof(p));
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    p.ws_cnt = reinterpret_cast<int *>(ws + pl.ws_cnt_off);
+    p.ws_hyb_cnt = reinterpret_cast<int *>(ws + pl.ws_hybcnt_off);
+    p.ws_hyb = reinterpret_cast<float *>(ws + pl.ws_hyb_off);
+    p.ws_part = reinterpret_cast<float *>(ws + pl.ws_part_off);
+    p.ws_csr = reinterpret_cast<float *>(ws + pl.ws_csr_off);
+    p.ws_acc = reinterpret_cast<float *>(ws + pl.ws_acc_off);
+    p.det = 0;
+    p.x = x; p.x_is_half = x_is_half; p.out = nullptr; p.y_is_half = y_is_half; p.bias = bias;
+    p.xw_world = xc->world; p.xw_rank = xc->rank; p.xw_members = xc->members; p.xw_nfull = xc->out_features_full;
+    p.xw_base = reinterpret_cast<const unsigned long long *>(xc->peer_base);
+    p.xw_out_off = xc->out_offset; p.xw_flag_off = xc->flag_offset; p.xw_state_off = xc->state_offset; p.xw_err_off = xc->error_offset;
     return launch<true>(a, pl, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -157,20 +157,18 @@ torch::Tensor workspace_for(const torch::Tensor &like, size_t bytes) {
     return it->second;
 }
 
-// y = bias + LUT-GEMV(x) [+ CSR] [+ dense rows]; x fp16/fp32 with numel == in; returns [out] in x's dtype
-// (QuantLinearLUT.forward's matvec branch, squeezellm/quant.py:212-312, in one launch).
-torch::Tensor lutgemv_fused(torch::Tensor x, torch::Tensor qweight, torch::Tensor lookup_table, int bits,
-                            c10::optional<torch::Tensor> bias, c10::optional<torch::Tensor> rows,
-                            c10::optional<torch::Tensor> cols, c10::optional<torch::Tensor> vals,
-                            c10::optional<torch::Tensor> full_rows, c10::optional<torch::Tensor> full_row_indices) {
-    const at::cuda::OptionalCUDAGuard guard(device_of(x));
+// shared argument checking / descriptor filling of the two fused entry points
+void fill_fused_args(sqllm_lutgemv_args &a, const float *&bias_p, const torch::Tensor &x, const torch::Tensor &qweight,
+                     const torch::Tensor &lookup_table, int bits, const c10::optional<torch::Tensor> &bias,
+                     const c10::optional<torch::Tensor> &rows, const c10::optional<torch::Tensor> &cols,
+                     const c10::optional<torch::Tensor> &vals, const c10::optional<torch::Tensor> &full_rows,
+                     const c10::optional<torch::Tensor> &full_row_indices) {
     TORCH_CHECK(x.is_cuda() && x.is_contiguous(), "x must be a contiguous CUDA tensor");
     TORCH_CHECK(x.scalar_type() == torch::kFloat16 || x.scalar_type() == torch::kFloat32, "x must be fp16 or fp32");
     TORCH_CHECK(bits == 3 || bits == 4, "bits must be 3 or 4");
     need(qweight, "qweight", torch::kInt32, x);
     need(lookup_table, "lookup_table", torch::kFloat32, x);
     TORCH_CHECK(qweight.dim() == 2 && qweight.size(0) % bits == 0, "qweight must be [in/32*bits, out]");
-    sqllm_lutgemv_args a;
     memset(&a, 0, sizeof(a));
     a.bits = bits;
     a.in_features = (int)(qweight.size(0) / bits * 32);
@@ -180,7 +178,7 @@ torch::Tensor lutgemv_fused(torch::Tensor x, torch::Tensor qweight, torch::Tenso
     TORCH_CHECK(lookup_table.numel() == (int64_t)a.out_features * (1 << bits), "lookup_table must be [out, 2^bits]");
     a.qweight = qweight.data_ptr<int32_t>();
     a.lookup_table = lookup_table.data_ptr<float>();
-    const float *bias_p = nullptr;
+    bias_p = nullptr;
     if (bias.has_value() && bias->defined()) {
         need(*bias, "bias", torch::kFloat32, x);
         TORCH_CHECK(bias->numel() == a.out_features, "bias must have out_features elements");
@@ -200,6 +198,18 @@ torch::Tensor lutgemv_fused(torch::Tensor x, torch::Tensor qweight, torch::Tenso
         a.full_row_indices = full_row_indices->data_ptr<int32_t>();
         a.topX = (int)full_rows->size(1);
     }
+}
+
+// y = bias + LUT-GEMV(x) [+ CSR] [+ dense rows]; x fp16/fp32 with numel == in; returns [out] in x's dtype
+// (QuantLinearLUT.forward's matvec branch, squeezellm/quant.py:212-312, in one launch).
+torch::Tensor lutgemv_fused(torch::Tensor x, torch::Tensor qweight, torch::Tensor lookup_table, int bits,
+                            c10::optional<torch::Tensor> bias, c10::optional<torch::Tensor> rows,
+                            c10::optional<torch::Tensor> cols, c10::optional<torch::Tensor> vals,
+                            c10::optional<torch::Tensor> full_rows, c10::optional<torch::Tensor> full_row_indices) {
+    const at::cuda::OptionalCUDAGuard guard(device_of(x));
+    sqllm_lutgemv_args a;
+    const float *bias_p;
+    fill_fused_args(a, bias_p, x, qweight, lookup_table, bits, bias, rows, cols, vals, full_rows, full_row_indices);
     const size_t need_ws = sqllm_workspace_bytes(bits, a.in_features, a.out_features, a.topX);
     TORCH_CHECK(need_ws > 0, "sqllm_workspace_bytes failed: ", sqllm_last_error());
     torch::Tensor ws = workspace_for(x, need_ws);
@@ -208,6 +218,31 @@ torch::Tensor lutgemv_fused(torch::Tensor x, torch::Tensor qweight, torch::Tenso
     const int rc = sqllm_lutgemv_fused(&a, x.data_ptr(), half, y.data_ptr(), half, bias_p, ws.data_ptr(), (size_t)ws.numel(), cur_stream());
     check_status(rc, "quant_cuda.lutgemv_fused");
     return y;
+}
+
+// Column shard with the exchange built in (include/sqllm_b200.h, sqllm_lutgemv_fused_exchange): the result is written into every
+// rank's symmetric arena; nothing is returned.  peer_base: address of the device array of arena base addresses.
+void lutgemv_fused_exchange(torch::Tensor x, torch::Tensor qweight, torch::Tensor lookup_table, int bits,
+                            c10::optional<torch::Tensor> bias, c10::optional<torch::Tensor> rows,
+                            c10::optional<torch::Tensor> cols, c10::optional<torch::Tensor> vals,
+                            c10::optional<torch::Tensor> full_rows, c10::optional<torch::Tensor> full_row_indices,
+                            int64_t peer_base, int64_t out_offset, int64_t flag_offset, int64_t state_offset, int64_t error_offset,
+                            int world, int rank, int members, int out_features_full) {
+    const at::cuda::OptionalCUDAGuard guard(device_of(x));
+    sqllm_lutgemv_args a;
+    const float *bias_p;
+    fill_fused_args(a, bias_p, x, qweight, lookup_table, bits, bias, rows, cols, vals, full_rows, full_row_indices);
+    const size_t need_ws = sqllm_workspace_bytes(bits, a.in_features, a.out_features, a.topX);
+    TORCH_CHECK(need_ws > 0, "sqllm_workspace_bytes failed: ", sqllm_last_error());
+    torch::Tensor ws = workspace_for(x, need_ws);
+    sqllm_exchange xc;
+    memset(&xc, 0, sizeof(xc));
+    xc.world = world; xc.rank = rank; xc.members = members; xc.out_features_full = out_features_full;
+    xc.peer_base = reinterpret_cast<const uint64_t *>(peer_base);
+    xc.out_offset = (size_t)out_offset; xc.flag_offset = (size_t)flag_offset; xc.state_offset = (size_t)state_offset; xc.error_offset = (size_t)error_offset;
+    const int half = x.scalar_type() == torch::kFloat16;
+    const int rc = sqllm_lutgemv_fused_exchange(&a, x.data_ptr(), half, half, bias_p, ws.data_ptr(), (size_t)ws.numel(), &xc, cur_stream());
+    check_status(rc, "quant_cuda.lutgemv_fused_exchange");
 }
 
 torch::Tensor unpack_indices(torch::Tensor qweight, int bits) {
@@ -243,6 +278,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("x"), py::arg("qweight"), py::arg("lookup_table"), py::arg("bits"), py::arg("bias") = py::none(),
           py::arg("rows") = py::none(), py::arg("cols") = py::none(), py::arg("vals") = py::none(),
           py::arg("full_rows") = py::none(), py::arg("full_row_indices") = py::none());
+    m.def("lutgemv_fused_exchange", &lutgemv_fused_exchange,
+          "fused matvec of a column shard that stores its result into every rank's symmetric arena (NVLink peer memory) and waits for the peers'",
+          py::arg("x"), py::arg("qweight"), py::arg("lookup_table"), py::arg("bits"), py::arg("bias"), py::arg("rows"), py::arg("cols"),
+          py::arg("vals"), py::arg("full_rows"), py::arg("full_row_indices"), py::arg("peer_base"), py::arg("out_offset"),
+          py::arg("flag_offset"), py::arg("state_offset"), py::arg("error_offset"), py::arg("world"), py::arg("rank"), py::arg("members"),
+          py::arg("out_features_full"));
     m.def("unpack_indices", &unpack_indices, "GPU unpack of the packed indices -> uint8 [in, out] (test hook)");
     m.def("abi_version", []() { return sqllm_abi_version(); });
     m.def("set_deterministic", [](bool on) { sqllm_set_deterministic(on ? 1 : 0); },

@@ -104,3 +104,57 @@ def exchange_stacked(y_local, members, rank, world, out=None, group=None):
     out.view(lead + (members, world, w))[..., rank, :] = y_local.reshape(lead + (members, w))
     dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     return out
+
+
+class PeerExchange:
+    """Arena in torch symmetric memory (peer-mapped over NVLink) + the bookkeeping `quant_cuda.lutgemv_fused_exchange`
+    needs: the kernel's finishing CTAs store their slice of y into every rank's arena and wait for the peers', so a
+    column-sharded layer needs no separate collective (include/sqllm_b200.h, sqllm_lutgemv_fused_exchange).
+
+    One arena per rank, identical layout everywhere: [0,8) arrival counter, [64,72) expected arrivals (local), [128,132)
+    error word, destination vectors from 4096 on (one per `name`, [members][out_features_full] in the activation dtype).
+    Consecutive exchanges must use different names (a fast rank may deliver the next result while a slow one still reads
+    the previous one).  All ranks must call `forward` in the same order."""
+
+    FLAG, STATE, ERROR, DATA = 0, 64, 128, 4096
+
+    def __init__(self, rank, world, device, arena_bytes=8 << 20, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world, self.device = rank, world, device
+        self.group = group if group is not None else dist.group.WORLD
+        self.arena = symm.empty(arena_bytes, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.arena, self.group)
+        self.arena.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)          # every arena is zeroed before anybody's kernel can touch it
+        self.peer_base = int(self.hdl.buffer_ptrs_dev)
+        self.offsets, self.next = {}, self.DATA
+        self.arena_bytes = arena_bytes
+
+    def _slot(self, name, members, n_full, dtype):
+        key = (name, members, n_full, dtype)
+        if key not in self.offsets:
+            nbytes = members * n_full * torch.empty(0, dtype=dtype).element_size()
+            off = self.next
+            self.next = (off + nbytes + 255) & ~255
+            if self.next > self.arena_bytes:
+                raise RuntimeError("PeerExchange arena exhausted")
+            view = self.arena[off:off + nbytes].view(dtype).view(members, n_full)
+            self.offsets[key] = (off, view)
+        return self.offsets[key]
+
+    def forward(self, layer, x, name, members, n_full):
+        """Run `layer` (this rank's column shard, possibly a stacked sibling group's layer) on x; returns the local
+        [members, n_full] vector holding every rank's slices once the launch has completed (stream order)."""
+        from .quant import quant_cuda
+        off, view = self._slot(name, members, n_full, x.dtype)
+        rows, cols, vals, fr, fri = layer._sparse_args()
+        quant_cuda.lutgemv_fused_exchange(x.contiguous().reshape(-1), layer.qweight, layer.lookup_table, layer.bits, layer.bias,
+                                          rows, cols, vals, fr, fri, self.peer_base, off, self.FLAG, self.STATE, self.ERROR,
+                                          self.world, self.rank, members, n_full)
+        return view
+
+    def error(self):
+        """True if some wait inside a kernel timed out (a peer never delivered)."""
+        return bool(self.arena[self.ERROR:self.ERROR + 4].view(torch.int32).item())

@@ -11,23 +11,21 @@
 //     one 3-row / 32-input group for 3-bit; strip = 64 output columns) is flattened strip-major and
 //     cut into equal contiguous chunks, one per CTA (stream-K): every SM gets the same number of
 //     bytes whatever the shape.  A CTA touches at most MAXSEG strips.
-//   * Warp roles (10 warps): 8 consumers, 1 TMA producer, 1 sparse warp.
-//       - producer: streams the CTA's packed rows with cp.async.bulk (TMA, L2 evict-first) into an
-//         mbarrier-guarded ring of NSTAGE stages (16 units each); it starts before the programmatic
-//         dependency on the previous kernel is resolved (PDL), so weight traffic of GEMV n+1 overlaps
-//         the tail of GEMV n.
-//       - consumers: wait on a stage, pull their 128-bit word-quads into registers, release the
-//         stage, and turn every 4-bit index into an LDS address with a single PRMT (the per-strip
-//         LUT is staged transposed [value][column-slot] in a 4 KB aligned table so that every lane
-//         owns one shared-memory bank: conflict-free gathers); products go into packed
-//         fma.rn.f32x2 accumulators.  No tensor cores: this is a gather-bound GEMV.
-//       - sparse warp: stages the CSR rows of the strips this CTA owns with cp.async, reduces them
-//         deterministically, and takes a slice of the topX dense rows.
+//   * Warp roles (default build, SQLLM_LDG=2): 8 consumer warps + 1 sparse warp, 72 registers, 3 CTAs per SM.
+//       - consumers: each lane streams its own 16 bytes per unit row with cp.async into a private ring in shared memory,
+//         PF positions ahead (the first PF before the programmatic dependency on the previous kernel resolves - PDL - so
+//         the weight traffic of GEMV n+1 overlaps the tail of GEMV n), pulls the word-quad into registers and turns every
+//         4-bit index into an LDS address with a single PRMT (the per-strip LUT is staged transposed
+//         [value][column-slot] in a 4 KB aligned table so that every lane owns one shared-memory bank: conflict-free
+//         gathers); products go into packed fma.rn.f32x2 accumulators.  No tensor cores: this is a gather-bound GEMV.
+//         (SQLLM_LDG=1: register ring fed by LDG.128; SQLLM_LDG=0: TMA producer warp + mbarrier ring - measured, not faster.)
+//       - sparse warp: CSR rows spread evenly over all CTAs, staged with 16-byte cp.async, x gathered in batches,
+//         per-row sums in storage order; plus a k-slice of the topX dense rows.
 //   * Only the slice of x a CTA needs is staged (fp32, converted from fp16 on the way in).
-//   * Flush: accumulate mode (the reference's 12 symbols; `mul` pre-filled by the caller) issues one
-//     red.add.f32 per (CTA, column).  Fused mode (QuantLinearLUT.forward fast path) writes partials
-//     to a workspace; the last-arriving CTA of each strip (atomic ticket, no spinning) sums them in
-//     fixed order, adds bias, converts and stores -> deterministic, no pre-zeroed output.
+//   * Flush: accumulate mode (the reference's 12 symbols; `mul` pre-filled by the caller) issues one red.add.f32 per
+//     (CTA, column).  Fused mode (QuantLinearLUT.forward): fast (default) = red.add into a workspace accumulator, a
+//     release counter, and the last CTAs of the grid convert / store y (optionally into every rank's peer-mapped arena:
+//     the multi-GPU exchange); deterministic = per-strip partials + tickets, fixed summation order.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>

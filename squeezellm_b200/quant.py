@@ -6,8 +6,9 @@ rows, cols, vals, full_rows, full_row_indices, startrows), `pack2`, `forward` an
 as the reference, so `llama.py`-style loaders work unchanged.  Differences, all behind the same API:
 
   * `forward` (batch-1 branch, reference quant.py:212-312) uses ONE fused launch
-    (`quant_cuda.lutgemv_fused`: fp16/fp32 x in, y out in x's dtype, bias + CSR + dense rows fused,
-    deterministic) instead of zeros + x.float() + 1-3 launches + y.to(dtype).  Set
+    (`quant_cuda.lutgemv_fused`: fp16/fp32 x in, y out in x's dtype, bias + CSR + dense rows fused;
+    `quant_cuda.set_deterministic(True)` selects the bit-reproducible summation) instead of
+    zeros + x.float() + 1-3 launches + y.to(dtype).  Set
     `QuantLinearLUT.use_fused = False` to go through the reference's 12 symbols exactly as quant.py does.
   * `balanced=True` raises NotImplementedError up front: the reference dispatches it to
     `vecquant{3,4}matmul_spmv_balanced_nuq_perchannel`, which its extension never defines

@@ -158,3 +158,107 @@ class PeerExchange:
     def error(self):
         """True if some wait inside a kernel timed out (a peer never delivered)."""
         return bool(self.arena[self.ERROR:self.ERROR + 4].view(torch.int32).item())
+
+
+class ShardedSiblingGroup:
+    """Column shards of a set of sibling layers (same input) run as ONE stacked launch per rank + ONE exchange.
+
+    Built from the full (unsharded) QuantLinearLUT members: every rank keeps columns [rank*w, (rank+1)*w) of each member
+    (`shard_state`), stacks those shards along N (`fusion.stack_buffers`) and answers the members' `forward(x)` through the
+    same one-result cache protocol as `fusion.SiblingGroup` - so model code is unchanged: `q_proj(x)`, `k_proj(x)`,
+    `v_proj(x)` return FULL-width vectors on every rank.  The exchange is `PeerExchange` (in-kernel stores over NVLink, no
+    collective) when one is given, else one NCCL all-reduce per stacked launch (`exchange_stacked`).
+    A single layer (o_proj, down_proj) is simply a group of one.  `compute` lets CPU tests stand in for the CUDA launch."""
+
+    def __init__(self, members, rank, world, name, peer=None, group=None, compute=None):
+        from .fusion import stack_buffers, _version
+        from .quant import QuantLinearLUT
+        self._version = _version
+        self.members, self.rank, self.world, self.name, self.peer, self.pg, self.compute = list(members), rank, world, name, peer, group, compute
+        n_full = {m.outfeatures for m in self.members}
+        if len(n_full) != 1:
+            raise ValueError("sibling layers sharded together must have the same out_features")
+        self.n_full = n_full.pop()
+        c0, c1 = shard_bounds(self.n_full, world)[rank]
+        if (c1 - c0) * world != self.n_full:
+            raise ValueError(f"out_features={self.n_full} does not split into {world} equal 4-aligned shards")
+        self.w = c1 - c0
+        shards = []
+        for m in self.members:
+            st = shard_state({k: v for k, v in m.state_dict().items()}, c0, c1)
+            s = QuantLinearLUT(m.bits, m.infeatures, self.w, "bias" in st, include_sparse="rows" in st,
+                               numvals=int(st["vals"].numel()) if "vals" in st else 0, topX=int(st["full_rows"].shape[1]) if "full_rows" in st else 0)
+            s.load_state_dict(st, strict=False)
+            shards.append(s.to(m.qweight.device))
+        b = stack_buffers(shards)
+        layer = QuantLinearLUT(b["bits"], b["infeatures"], b["outfeatures"], b["bias"] is not None, include_sparse="rows" in b)
+        layer.qweight, layer.lookup_table = b["qweight"], b["lookup_table"]
+        if b["bias"] is not None:
+            layer.bias = b["bias"]
+        if "rows" in b:
+            for k in ("rows", "cols", "vals"):
+                layer.register_buffer(k, b[k])
+            layer.numvals = int(b["vals"].numel())
+        if "full_rows" in b:
+            layer.register_buffer("full_rows", b["full_rows"])
+            layer.register_buffer("full_row_indices", b["full_row_indices"])
+            layer.topX = int(b["full_rows"].shape[1])
+        self.layer = layer
+        for i, (m, o) in enumerate(zip(self.members, b["offsets"])):
+            # the member keeps its buffer names but now holds this rank's shard (views of the stacked storage)
+            m.qweight = layer.qweight[:, o:o + self.w]
+            m.lookup_table = layer.lookup_table[o:o + self.w]
+            for k in ("rows", "cols", "vals", "full_rows", "full_row_indices"):
+                if hasattr(m, k):
+                    delattr(m, k)
+            m.include_sparse, m.numvals, m.topX = False, 0, 0
+            if m.bias is not None:
+                m.bias = layer.bias[o:o + self.w]
+            object.__setattr__(m, "_sibling_group", (self, i))
+        self._x = self._ver = self._y = None
+        self._pending = set()
+        self.launches = 0
+
+    def _run(self, x):
+        nm = len(self.members)
+        if self.compute is not None:
+            y = self.compute(self.layer, x)
+        elif self.peer is not None and x.shape[-1] == x.numel():
+            return self.peer.forward(self.layer, x, self.name, nm, self.n_full)       # [members, n_full], exchange done in-kernel
+        else:
+            y = self.layer(x)
+        return exchange_stacked(y, nm, self.rank, self.world, group=self.pg)            # [..., members, n_full]
+
+    def member_forward(self, i, x):
+        if not (self._x is x and self._ver == self._version(x) and i in self._pending):
+            self._y = self._run(x)
+            self._x, self._ver = x, self._version(x)
+            self._pending = set(range(len(self.members)))
+            self.launches += 1
+        self._pending.discard(i)
+        y = self._y[..., i, :]
+        if y.dim() < x.dim():                      # decode-shaped input [1, 1, K] -> [1, 1, N] like QuantLinearLUT.forward
+            y = y.reshape(x.shape[:-1] + (self.n_full,))
+        if not self._pending:
+            self._x = self._y = None
+        return y
+
+
+def shard_model(model, rank, world, peer=None, group=None, siblings=(("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj"))):
+    """Column-shard every QuantLinearLUT of `model` in place for rank `rank` of `world`: sibling sets become one
+    ShardedSiblingGroup each, every other QuantLinearLUT a group of one.  Every rank must call it on the same model.
+    Returns the groups (their `.launches` count stacked launches).  Exchange names alternate so that consecutive launches
+    never share a destination (PeerExchange's requirement)."""
+    from .quant import QuantLinearLUT
+    groups = []
+    for mod_name, mod in model.named_modules():
+        taken = set()
+        for names in siblings:
+            ms = [getattr(mod, n, None) for n in names]
+            if all(isinstance(m, QuantLinearLUT) and m._sibling_group is None for m in ms) and len({m.outfeatures for m in ms}) == 1:
+                groups.append(ShardedSiblingGroup(ms, rank, world, f"{mod_name}.{'+'.join(names)}", peer=peer, group=group))
+                taken.update(names)
+        for n, child in mod.named_children():
+            if isinstance(child, QuantLinearLUT) and n not in taken and child._sibling_group is None:
+                groups.append(ShardedSiblingGroup([child], rank, world, f"{mod_name}.{n}", peer=peer, group=group))
+    return groups

@@ -159,3 +159,66 @@ def test_stacked_shard_exchange_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(a and b for _, a, b in res), res
+
+
+def _layer_dict(m):
+    """QuantLinearLUT (CPU buffers) -> the oracle's layer dict."""
+    d = dict(bits=m.bits, infeatures=m.infeatures, outfeatures=m.outfeatures, qweight=m.qweight.contiguous().numpy(),
+             lookup_table=m.lookup_table.contiguous().numpy(), bias=m.bias.numpy() if m.bias is not None else None)
+    for k in ("rows", "cols", "vals", "full_rows", "full_row_indices"):
+        d[k] = getattr(m, k).numpy() if hasattr(m, k) else None
+    return d
+
+
+def _worker_shard_model(rank, world, port, q):
+    import torch.distributed as dist
+    from squeezellm_b200.quant import QuantLinearLUT
+    from squeezellm_b200.sharding import shard_model
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def member(L, sparse, topx):
+            m = QuantLinearLUT(L["bits"], L["infeatures"], L["outfeatures"], False, include_sparse=sparse,
+                               numvals=len(L["vals"]) if sparse else 0, topX=topx)
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in L.items() if isinstance(v, np.ndarray) and k in m.state_dict()}, strict=False)
+            return m
+
+        class Attn(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.full = {}
+                for i, n in enumerate(("q_proj", "k_proj", "v_proj", "o_proj")):
+                    L = orc.make_layer(4, 128, 64, sparsity=0.05, topX=3, seed=40 + i, nonzero_full_rows=True)
+                    self.full[n] = L
+                    setattr(self, n, member(L, True, 3))
+
+        attn = Attn()
+        groups = shard_model(attn, rank, world)
+        for g in groups:  # CPU stand-in for the CUDA launch of the stacked shard
+            g.compute = lambda layer, xx: torch.from_numpy(orc.forward_f64(_layer_dict(layer), xx.numpy().reshape(1, -1)).astype(np.float32))
+        x = torch.from_numpy(orc.make_vec(128, seed=5)).reshape(1, 128)
+        outs = {n: getattr(attn, n)(x).numpy() for n in ("q_proj", "k_proj", "v_proj", "o_proj")}
+        ok = all(rel_err(outs[n], orc.forward_f64(attn.full[n], x.numpy())) < TIGHT_TOL for n in outs)
+        shapes = sorted((len(g.members), g.launches, g.w) for g in groups)
+        q.put((rank, ok, shapes, attn.q_proj.qweight.shape[1]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_model_world2_gloo():
+    """shard_model: q/k/v become one stacked shard + one exchange, o_proj a group of one; every rank gets full-width outputs."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_shard_model, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, shapes, width in res:
+        assert ok, f"rank {rank}"
+        assert shapes == [(1, 1, 32), (3, 1, 32)], shapes     # o_proj alone (1 launch), q/k/v together (1 launch), 32 columns per rank
+        assert width == 32                                     # members now hold this rank's shard

@@ -365,7 +365,7 @@ def main():
                 SiblingGroup([L[n] for n in names])
                 nlaunch -= len(names) - 1
         torch.cuda.empty_cache()
-    exchange_used = "none"
+    exchange_used, peer_used = "none", None
     if world > 1:
         import torch.distributed as dist
         step_nccl = make_step(layers, world)
@@ -388,7 +388,7 @@ def main():
             vote = torch.tensor([ok], device=dev)
             dist.all_reduce(vote, op=dist.ReduceOp.MIN)  # every rank takes the same decision
             if vote.item() == 1.0:
-                step, exchange_used = step_p2p, "in-kernel stores to every rank's symmetric arena over NVLink (no collective)"
+                step, exchange_used, peer_used = step_p2p, "in-kernel stores to every rank's symmetric arena over NVLink (no collective)", peer
             elif why or rank == 0:
                 print(f"[bench] rank {rank}: p2p exchange not used ({why or 'another rank declined'}); falling back to NCCL", file=sys.stderr)
     else:
@@ -459,6 +459,9 @@ def main():
         barrier()
         e2e_ms = ev0.elapsed_time(ev1)
 
+    if peer_used is not None and peer_used.error():  # a bounded in-kernel wait gave up: the numbers of this run are not valid
+        exchange_used += " - ERROR: a peer wait timed out during this run"
+        print(f"[bench] rank {rank}: exchange error word is set", file=sys.stderr)
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)

@@ -47,7 +47,7 @@ extern "C" {
 #define SQLLM_ECUDA (-2)    /* a CUDA runtime call or launch failed */
 #define SQLLM_EWORKSPACE (-3) /* workspace missing or too small */
 
-#define SQLLM_ABI_VERSION 1
+#define SQLLM_ABI_VERSION 2   /* 2: + sqllm_lutgemv_fused_exchange, sqllm_set_deterministic */
 
 int sqllm_abi_version(void);
 const char *sqllm_last_error(void);

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     lib = load_lib()
-    assert lib.sqllm_abi_version() == 1
+    assert lib.sqllm_abi_version() == 2
     assert isinstance(lib.sqllm_last_error(), bytes)
 
 
@@ -68,7 +68,7 @@ def test_quant_cuda_module_has_the_reference_names():
     for s in REFERENCE_SYMBOLS:
         assert callable(getattr(quant_cuda, s))
     assert not any("balanced" in n for n in dir(quant_cuda))  # absent in the reference build too
-    assert quant_cuda.abi_version() == 1
+    assert quant_cuda.abi_version() == 2
 
 
 def test_quant_cuda_rejects_cpu_tensors_loudly():
@@ -80,3 +80,25 @@ def test_quant_cuda_rejects_cpu_tensors_loudly():
         quant_cuda.vecquant4matmul_nuq_perchannel(x, q, y, lut)
     with pytest.raises(RuntimeError):
         quant_cuda.lutgemv_fused(x, q, lut, 4)
+
+
+class Exchange(ctypes.Structure):  # mirrors sqllm_exchange
+    _fields_ = [("world", ctypes.c_int), ("rank", ctypes.c_int), ("members", ctypes.c_int), ("out_features_full", ctypes.c_int),
+                ("peer_base", ctypes.c_void_p), ("out_offset", ctypes.c_size_t), ("flag_offset", ctypes.c_size_t),
+                ("state_offset", ctypes.c_size_t), ("error_offset", ctypes.c_size_t)]
+
+
+@pytest.mark.parametrize("change,frag", [(dict(rank=2), b"rank"), (dict(members=3), b"members"), (dict(out_features_full=64), b"out_features_full"),
+                                         (dict(peer_base=0), b"peer_base"), (dict(out_offset=4100), b"misaligned"), (dict(flag_offset=4), b"misaligned")])
+def test_exchange_descriptor_validation_without_gpu(change, frag):
+    """sqllm_lutgemv_fused_exchange rejects inconsistent descriptors before it touches the device."""
+    lib = load_lib()
+    lib.sqllm_lutgemv_fused_exchange.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    a = Args(bits=4, in_features=128, out_features=128, batch=1, qweight=16, lookup_table=16)
+    x = Exchange(world=2, rank=0, members=2, out_features_full=128, peer_base=16, out_offset=4096, flag_offset=0, state_offset=64, error_offset=128)
+    for k, v in change.items():
+        setattr(x, k, v)
+    rc = lib.sqllm_lutgemv_fused_exchange(ctypes.byref(a), 16, 1, 1, None, 16, 1 << 20, ctypes.byref(x), None)
+    assert rc == -1 and frag in lib.sqllm_last_error(), lib.sqllm_last_error()
+    assert lib.sqllm_lutgemv_fused_exchange(ctypes.byref(a), 16, 1, 1, None, 16, 1 << 20, None, None) == -1

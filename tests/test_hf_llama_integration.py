@@ -77,3 +77,61 @@ def test_hf_llama_forward_is_unchanged_by_sibling_stacking(tiny_llama, seq):
     assert calls_unfused == 14 and FakeQuantCuda.calls == 8, "7 launches per block become 4"
     assert all(g.launches == 1 for g in groups)
     assert torch.allclose(before, after, rtol=1e-5, atol=1e-6)
+
+
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker_sharded_llama(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    from squeezellm_b200.sharding import shard_model
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfg = transformers.LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                                       num_key_value_heads=4, vocab_size=97, max_position_embeddings=32)
+        torch.manual_seed(0)
+        model = transformers.LlamaForCausalLM(cfg).eval()
+        state = {k: v.clone() for k, v in model.state_dict().items()}
+        for n, (name, lin) in enumerate((k, v) for k, v in ck.find_linear_layers(model).items() if k != "lm_head"):
+            L = orc.make_layer(4, lin.in_features, lin.out_features, seed=100 + n)
+            del state[name + ".weight"]
+            state[name + ".qweight"] = torch.from_numpy(L["qweight"])
+            state[name + ".lookup_table"] = torch.from_numpy(L["lookup_table"] * 5.0)
+        ck.load_quantized(model, state, 4)
+        Q.quant_cuda = FakeQuantCuda()
+        out = []
+        with torch.no_grad():
+            for ids in (torch.tensor([[5]]), torch.tensor([[5, 17, 42]])):
+                out.append(model(ids).logits)
+            groups = shard_model(model, rank, world)
+            for i, ids in enumerate((torch.tensor([[5]]), torch.tensor([[5, 17, 42]]))):
+                out.append(model(ids).logits)
+        same = all(torch.allclose(out[i], out[i + 2], rtol=1e-5, atol=1e-6) for i in range(2))
+        q.put((rank, same, len(groups), sorted({g.w for g in groups}), model.model.layers[0].self_attn.q_proj.qweight.shape[1]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_hf_llama_forward_is_unchanged_by_shard_model_world2_gloo():
+    """shard_model on the real HF module tree: every rank keeps half of every QuantLinearLUT's columns, runs stacked shards and one
+    exchange per launch (gloo all-reduce here), and the unmodified forward still produces the unsharded logits on every rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded_llama, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same, ngroups, widths, qcols in res:
+        assert same, f"rank {rank}: sharded logits differ"
+        assert ngroups == 8 and widths == [32, 64] and qcols == 32   # per block: q/k/v, o, gate/up, down; hidden 64 -> 32, ffn 128 -> 64 per rank

@@ -102,3 +102,26 @@ def test_exchange_descriptor_validation_without_gpu(change, frag):
     rc = lib.sqllm_lutgemv_fused_exchange(ctypes.byref(a), 16, 1, 1, None, 16, 1 << 20, ctypes.byref(x), None)
     assert rc == -1 and frag in lib.sqllm_last_error(), lib.sqllm_last_error()
     assert lib.sqllm_lutgemv_fused_exchange(ctypes.byref(a), 16, 1, 1, None, 16, 1 << 20, None, None) == -1
+
+
+def test_reference_quant_py_imports_against_our_extension():
+    """Option A of INTEGRATION.md: the reference's own squeezellm/quant.py, unmodified, imports `quant_cuda` by name and finds every
+    symbol it calls in OUR extension (except the *_balanced_* ones, which the reference's extension does not define either).
+    Needs the reference checkout; skipped where it is absent (e.g. on the GPU box)."""
+    import importlib.util
+    import os
+    import re
+    ref = "/root/reference/squeezellm/quant.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference checkout not present")
+    import squeezellm_b200.quant as ours            # puts the in-tree extension directory on sys.path, imports quant_cuda
+    spec = importlib.util.spec_from_file_location("reference_quant", ref)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                     # runs `import quant_cuda` (quant.py:5)
+    assert mod.quant_cuda is ours.quant_cuda
+    called = set(re.findall(r"quant_cuda\.(\w+)", open(ref).read()))
+    missing = {n for n in called if not hasattr(mod.quant_cuda, n)}
+    assert len(called - missing) == 12
+    assert missing and all("balanced" in n for n in missing), missing
+    m = mod.QuantLinearLUT(4, 128, 128, False, include_sparse=True, numvals=5, topX=10)   # the reference's module over our extension
+    assert set(m.state_dict()) == set(ours.QuantLinearLUT(4, 128, 128, False, include_sparse=True, numvals=5, topX=10).state_dict())

@@ -47,7 +47,7 @@ extern "C" {
 #define SQLLM_ECUDA (-2)    /* a CUDA runtime call or launch failed */
 #define SQLLM_EWORKSPACE (-3) /* workspace missing or too small */
 
-#define SQLLM_ABI_VERSION 2   /* 2: + sqllm_lutgemv_fused_exchange, sqllm_set_deterministic */
+#define SQLLM_ABI_VERSION 3   /* 2: + sqllm_lutgemv_fused_exchange, sqllm_set_deterministic ; 3: + sqllm_set_lut_mode, sqllm_workspace_error */
 
 int sqllm_abi_version(void);
 const char *sqllm_last_error(void);
@@ -94,6 +94,23 @@ int sqllm_lutgemv(const sqllm_lutgemv_args *args, void *stream);
  *   1: per-strip partials reduced in a fixed order by the last-arriving contributor - bit-reproducible, 1.3-2x slower on
  *     layers with outliers. */
 void sqllm_set_deterministic(int on);
+
+/* Look-up-table precision of the fused path (process-wide; the 12 reference launchers below always use the exact table).
+ *   SQLLM_LUT_EXACT (default): the per-channel codebook is used as stored, fp32 (squeezellm/quant_cuda_kernel.cu:779,866).
+ *   SQLLM_LUT_FP16_PAIR      : north_star's "per-channel fp16 LUT" - centroids are rounded to fp16 (round-to-nearest-even) when a
+ *     CTA builds its shared-memory table, which then holds PAIRS of centroids: one shared-memory read serves two weights and
+ *     the products run as fp16 x fp16 -> fp32 FMAs (exact products, fp32 accumulation).  Only taken when x is fp16 (an fp32 x
+ *     silently keeps the exact table); centroids must be finite in fp16 (|v| <= 65504).  Error against the exact result is that
+ *     of the centroid rounding alone: <= 2^-11 relative per weight, ~2.5e-4 of max|y| on 4096-wide layers (tests/test_lut_fp16.py
+ *     states and checks the bounds).  Environment: SQLLM_LUT_MODE=fp16.  Do not switch while other threads launch. */
+#define SQLLM_LUT_EXACT 0
+#define SQLLM_LUT_FP16_PAIR 1
+void sqllm_set_lut_mode(int mode);
+int sqllm_get_lut_mode(void);
+
+/* Reads the workspace's error word (synchronises `stream`): 1 if a bounded in-kernel wait (2 s) ever gave up on this workspace -
+ * the result of that call, and possibly later ones, is incomplete - else 0; negative on failure. */
+int sqllm_workspace_error(const void *workspace, void *stream);
 
 /* Fused module path behind QuantLinearLUT.forward (squeezellm/quant.py:211-312), batch-1 decode:
  *   y[c] = bias[c] + LUT-GEMV + CSR + dense rows, written (not accumulated) as fp16 or fp32,

@@ -35,6 +35,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -227,14 +228,14 @@ __device__ __forceinline__ int ticket_take(int *counter) {
 #define DBG(p) 0
 #endif
 #ifdef SQLLM_TRACE
-__device__ __forceinline__ void trace_mark(const Params &p, int slot) {
-    if (p.trace) {
+__device__ __forceinline__ void trace_mark(unsigned long long *trace, int slot) {
+    if (trace) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.trace[(size_t)blockIdx.x * 32 + slot] = t;
+        trace[(size_t)blockIdx.x * 32 + slot] = t;
     }
 }
-#define TRACE(slot, cond) do { if (cond) trace_mark(p, slot); } while (0)
+#define TRACE(slot, cond) do { if (cond) trace_mark(p.trace, slot); } while (0)
 #else
 #define TRACE(slot, cond) do { } while (0)
 #endif
@@ -1273,6 +1274,15 @@ __global__ void unpack_kernel(int bits, const uint32_t *__restrict__ q, int K, i
     }
 }
 
+#include "lutgemv_v2.cuh"
+
+// shared-window address at which a kernel without static shared memory sees its dynamic shared memory (the v2 carve-up aligns
+// tables to their own size - up to 64 KB - so the host needs the real address, not a worst case; the kernel re-checks it)
+__global__ void smem_base_probe(unsigned *out) {
+    extern __shared__ unsigned char probe_smem[];
+    *out = smem_u32(probe_smem);
+}
+
 // =================================================================================================
 // Host side
 // =================================================================================================
@@ -1290,10 +1300,16 @@ struct DevInfo {
     int sm = 0;
     bool attr_set = false;
 };
+// Process-wide state (mode switches, lazily read environment knobs, per-device attributes) is guarded by g_state_mu: the entry
+// points may be called from several host threads.  Switching a mode (sqllm_set_deterministic / sqllm_set_lut_mode) while other
+// threads are launching is allowed but takes effect per call; do not switch while a CUDA graph that should keep the old mode is
+// being captured.
+std::recursive_mutex g_state_mu;
 DevInfo g_dev[64];
 int g_use_pdl = -1;
 int g_det = -1;
 int det_mode() {
+    std::lock_guard<std::recursive_mutex> lk(g_state_mu);
     if (g_det < 0) { const char *e = getenv("SQLLM_DETERMINISTIC"); g_det = (e && e[0] == '1') ? 1 : 0; }
     return g_det;
 }
@@ -1353,6 +1369,7 @@ struct Plan {
 };
 
 int make_plan(int bits, int K, int N, int topX, bool has_csr_in, bool fused, Plan &pl) {
+    std::lock_guard<std::recursive_mutex> state_lock(g_state_mu);  // lazily initialised statics below
     const bool has_csr = has_csr_in || topX > 0;  // from here on: "a staging buffer is needed"
     // staging: CSR cols/vals chunks (8 KB); the deterministic fused mode also stages the dense-row partials there (8 KB more)
     pl.has_stage = has_csr ? CSR_CH * 8 + ((fused && det_mode() == 1) ? CSR_CH * 8 : 0) : 0;
@@ -1503,6 +1520,7 @@ int check_common(const sqllm_lutgemv_args *a) {
 
 template <int BITS, bool FUSED>
 cudaError_t launch_kernel(const Plan &pl, const Params &p, const CUtensorMap &tm, cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> state_lock(g_state_mu);
     if (g_use_pdl < 0) {
         const char *e = getenv("SQLLM_NO_PDL");
         g_use_pdl = (e && e[0] == '1') ? 0 : 1;
@@ -1524,6 +1542,7 @@ cudaError_t launch_kernel(const Plan &pl, const Params &p, const CUtensorMap &tm
 
 template <bool FUSED>
 int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> state_lock(g_state_mu);
     p.qw = reinterpret_cast<const uint32_t *>(a->qweight);
     p.lut = a->lookup_table;
     p.rows = a->rows; p.cols = a->cols; p.vals = a->vals;
@@ -1565,6 +1584,184 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
     return SQLLM_OK;
 }
 
+
+// =================================================================================================
+// v2 (lutgemv_v2.cuh): plan + launch.  One CTA per SM; all process-wide state behind one mutex / atomics.
+// =================================================================================================
+bool g_v2_attr[64] = {};
+int g_lut_mode = -1;     // 0: exact fp32 table, 1: fp16 pair table when x is fp16 (SQLLM_LUT_MODE=fp16 / sqllm_set_lut_mode)
+int g_kernel_sel = -1;   // 2: v2 (default), 1: v1 everywhere (SQLLM_KERNEL=v1; kept for A/B runs and as the deterministic mode's kernel)
+
+int lut_mode() {
+    std::lock_guard<std::recursive_mutex> lk(g_state_mu);
+    if (g_lut_mode < 0) {
+        const char *e = getenv("SQLLM_LUT_MODE");
+        g_lut_mode = (e && (!strcmp(e, "fp16") || !strcmp(e, "pair") || !strcmp(e, "1"))) ? 1 : 0;
+    }
+    return g_lut_mode;
+}
+int kernel_sel() {
+    std::lock_guard<std::recursive_mutex> lk(g_state_mu);
+    if (g_kernel_sel < 0) {
+        const char *e = getenv("SQLLM_KERNEL");
+        g_kernel_sel = (e && !strcmp(e, "v1")) ? 1 : 2;
+    }
+    return g_kernel_sel;
+}
+
+typedef void (*K2)(const v2::P2, const CUtensorMap, const CUtensorMap);
+struct K2Info { K2 fn; int tab, stage; };
+// [bits==4][variant][fused] ; variant 0: exact, fp32 x ; 1: exact, fp16 x ; 2: fp16 pair table, fp16 x
+K2Info k2_lookup(int bits, int variant, bool fused) {
+#define K2E(B, M, XH, F) K2Info{v2::lutgemv2_kernel<B, M, XH, F>, v2::C2<B, M>::TAB, v2::C2<B, M>::STAGE}
+    if (bits == 4) {
+        if (variant == 0) return fused ? K2E(4, 0, false, true) : K2E(4, 0, false, false);
+        if (variant == 1) return fused ? K2E(4, 0, true, true) : K2E(4, 0, true, false);
+        return fused ? K2E(4, 1, true, true) : K2E(4, 1, true, false);
+    }
+    if (variant == 0) return fused ? K2E(3, 0, false, true) : K2E(3, 0, false, false);
+    if (variant == 1) return fused ? K2E(3, 0, true, true) : K2E(3, 0, true, false);
+    return fused ? K2E(3, 1, true, true) : K2E(3, 1, true, false);
+#undef K2E
+}
+
+struct Plan2 {
+    int R, strips, T, chunk, G, nstage, smem, hc, hrows, csr_rpc;
+    unsigned smem_raw;
+};
+unsigned g_smem_raw[64] = {};
+
+int make_plan2(int bits, int K, int N, int topX, int variant, bool fused, Plan2 &pl, K2Info &ki) {
+    int dev = 0, sm = 0;
+    unsigned smem_raw = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(SQLLM_ECUDA, "cudaGetDevice failed");
+    if (dev < 0 || dev >= 64) return fail(SQLLM_EINVAL, "device ordinal %d out of range", dev);
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_state_mu);
+        DevInfo &d = g_dev[dev];
+        if (d.sm == 0 && (cudaDeviceGetAttribute(&d.sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.sm <= 0)) {
+            d.sm = 0;
+            return fail(SQLLM_ECUDA, "cannot query SM count");
+        }
+        sm = d.sm;
+        if (!g_v2_attr[dev]) {
+            for (int b = 3; b <= 4; ++b)
+                for (int v = 0; v < 3; ++v)
+                    for (int f = 0; f < 2; ++f)
+                        if (cudaFuncSetAttribute(k2_lookup(b, v, f != 0).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                            return fail(SQLLM_ECUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+            // one-time probe (synchronous; refused during stream capture, so the first call must come before capture - any warm-up does)
+            unsigned *d_out = nullptr, h_out = 0;
+            cudaError_t pe = cudaMalloc(&d_out, sizeof(unsigned));
+            if (pe == cudaSuccess) {
+                smem_base_probe<<<1, 1, 1024>>>(d_out);
+                pe = cudaMemcpy(&h_out, d_out, sizeof(unsigned), cudaMemcpyDeviceToHost);
+                cudaFree(d_out);
+            }
+            if (pe != cudaSuccess || h_out == 0) {
+                cudaGetLastError();
+                return fail(SQLLM_ECUDA, "shared-memory probe failed (first call inside a stream capture? run one call before capturing): %s", cudaGetErrorString(pe));
+            }
+            g_smem_raw[dev] = h_out;
+            g_v2_attr[dev] = true;
+        }
+        smem_raw = g_smem_raw[dev];
+    }
+    ki = k2_lookup(bits, variant, fused);
+    pl.R = bits == 4 ? K / 8 : K / 32;
+    pl.strips = (N + STRIP - 1) / STRIP;
+    const long long T = (long long)pl.strips * pl.R;
+    if (T > 0x3fffffff) return fail(SQLLM_EINVAL, "problem too large");
+    if (fused && N > MAX_N_FUSED) return fail(SQLLM_EINVAL, "out_features=%d exceeds the fused accumulator (max %d)", N, MAX_N_FUSED);
+    pl.T = (int)T;
+    int chunk = (int)(2 * ((T + 2LL * sm - 1) / (2LL * sm)));
+    if (chunk < 2) chunk = 2;
+    pl.chunk = chunk;
+    pl.G = (int)((T + chunk - 1) / chunk);
+    // shared memory, exactly as lutgemv2_kernel carves it: [fixed][x][ring stages ...][table 0][table 1][... ring stages]
+    const unsigned raw = smem_raw;
+    const unsigned base = (raw + 127u) & ~127u;
+    const unsigned lo_base = base + v2::OFF_X + (unsigned)((K * (variant == 0 ? 4 : 2) + 127) & ~127);
+    const unsigned tab0 = (lo_base + (unsigned)ki.tab - 1u) & ~((unsigned)ki.tab - 1u);
+    const long long limit = (long long)raw + 227 * 1024;
+    const long long hi_room = limit - ((long long)tab0 + 2LL * ki.tab);
+    if (hi_room < 0) return fail(SQLLM_EINVAL, "in_features=%d does not fit the shared-memory carve-up of this table mode", K);
+    const int lo_cap = (int)((tab0 - lo_base) / (unsigned)ki.stage), hi_cap = (int)(hi_room / ki.stage);
+    int n = (chunk + v2::SU2 - 1) / v2::SU2 + 1;
+    if (n > v2::MAXD) n = v2::MAXD;
+    if (n > lo_cap + hi_cap) n = lo_cap + hi_cap;
+    if (n < 2) return fail(SQLLM_EINVAL, "in_features=%d leaves no room for a weight ring in shared memory", K);
+    const int n_lo = n < lo_cap ? n : lo_cap;
+    pl.nstage = n;
+    pl.smem = (int)((long long)tab0 + 2LL * ki.tab + (long long)(n - n_lo) * ki.stage - raw);
+    pl.smem_raw = raw;
+    pl.csr_rpc = (N + pl.G - 1) / pl.G;
+    pl.hc = pl.hrows = 0;
+    if (topX > 0) {
+        pl.hrows = (K + pl.G - 1) / pl.G;
+        pl.hc = (K + pl.hrows - 1) / pl.hrows;
+    }
+    return SQLLM_OK;
+}
+
+int launch2(const sqllm_lutgemv_args *a, int variant, bool fused, v2::P2 &p, cudaStream_t st) {
+    const bool hyb = a->full_rows && a->topX > 0;
+    Plan2 pl;
+    K2Info ki;
+    const int rc = make_plan2(a->bits, a->in_features, a->out_features, hyb ? a->topX : 0, variant, fused, pl, ki);
+    if (rc) return rc;
+    p.qw = reinterpret_cast<const uint32_t *>(a->qweight);
+    p.lut = a->lookup_table;
+    p.rows = a->rows; p.cols = a->cols; p.vals = a->vals;
+    p.full_rows = hyb ? a->full_rows : nullptr;
+    p.fri = hyb ? a->full_row_indices : nullptr;
+    p.topX = hyb ? a->topX : 0;
+    p.K = a->in_features; p.N = a->out_features;
+    p.R = pl.R; p.T = pl.T; p.chunk = pl.chunk; p.nstage = pl.nstage; p.smem_raw = pl.smem_raw;
+    p.hc = hyb ? pl.hc : 0; p.hrows = pl.hrows;
+    p.csr_rpc = pl.csr_rpc;
+    p.csr_al16 = (a->rows && ((reinterpret_cast<uintptr_t>(a->cols) | reinterpret_cast<uintptr_t>(a->vals)) & 15) == 0) ? 1 : 0;
+    p.strips = pl.strips;
+    p.nown_ctas = 0;
+    if (p.xw_world)
+        for (int b = 0; b < pl.G; ++b) {  // CTAs in whose range at least one strip starts
+            const long long c0 = (long long)b * pl.chunk, c1 = std::min<long long>(pl.T, c0 + pl.chunk);
+            if ((c0 + pl.R - 1) / pl.R < (c1 + pl.R - 1) / pl.R) ++p.nown_ctas;
+        }
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_state_mu);
+        p.trace = g_trace;
+        if (g_trace) g_trace += g_trace_stride;
+        g_last_grid = pl.G;
+        if (g_use_pdl < 0) {
+            const char *e = getenv("SQLLM_NO_PDL");
+            g_use_pdl = (e && e[0] == '1') ? 0 : 1;
+        }
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(pl.G);
+    cfg.blockDim = dim3(v2::THREADS2);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    // two tensor maps over the packed matrix: 64 columns x (32 units | 2 units) boxes
+    const int rows_per_unit = a->bits == 4 ? 1 : 3, qrows = a->in_features / 32 * a->bits;
+    CUtensorMap tm_big, tm_small;
+    // (a matrix shorter than one full stage never issues the big box; its map is clamped so that the encoder accepts it)
+    int trc = get_tensor_map(a->qweight, qrows, a->out_features, qrows < v2::SU2 * rows_per_unit ? 2 * rows_per_unit : v2::SU2 * rows_per_unit, tm_big);
+    if (trc) return trc;
+    trc = get_tensor_map(a->qweight, qrows, a->out_features, 2 * rows_per_unit, tm_small);
+    if (trc) return trc;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, ki.fn, p, tm_big, tm_small);
+    if (e != cudaSuccess) return fail(SQLLM_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return SQLLM_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -1573,7 +1770,23 @@ int launch(const sqllm_lutgemv_args *a, const Plan &pl, Params &p, cudaStream_t 
 extern "C" {
 
 int sqllm_abi_version(void) { return SQLLM_ABI_VERSION; }
-void sqllm_set_deterministic(int on) { g_det = on ? 1 : 0; }
+void sqllm_set_deterministic(int on) {
+    std::lock_guard<std::recursive_mutex> lk(g_state_mu);
+    g_det = on ? 1 : 0;
+}
+void sqllm_set_lut_mode(int mode) {
+    std::lock_guard<std::recursive_mutex> lk(g_state_mu);
+    g_lut_mode = mode == SQLLM_LUT_FP16_PAIR ? 1 : 0;
+}
+int sqllm_get_lut_mode(void) { return lut_mode(); }
+int sqllm_workspace_error(const void *workspace, void *stream) {
+    if (!workspace) return fail(SQLLM_EINVAL, "null workspace");
+    int flag = 0;
+    if (cudaMemcpyAsync(&flag, static_cast<const unsigned char *>(workspace) + 64, 4, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)) != cudaSuccess ||
+        cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess)
+        return fail(SQLLM_ECUDA, "cannot read the workspace error word: %s", cudaGetErrorString(cudaGetLastError()));
+    return flag ? 1 : 0;
+}
 
 // debug hook (not in the public header): successive launches write their timeline at buf, buf+stride, ...
 void sqllm_debug_set_trace(unsigned long long *buf, size_t stride_words) { g_trace = buf; g_trace_stride = stride_words; }
@@ -1605,6 +1818,17 @@ int sqllm_lutgemv(const sqllm_lutgemv_args *a, void *stream) {
     if (a->batch < 1) return fail(SQLLM_EINVAL, "batch must be >= 1");
     if (reinterpret_cast<uintptr_t>(a->vec) & 15) return fail(SQLLM_EINVAL, "vec must be 16-byte aligned");
     const bool hyb = a->full_rows && a->topX > 0;
+    if (kernel_sel() == 2 && a->out_features >= STRIP) {
+        v2::P2 q;
+        memset(&q, 0, sizeof(q));
+        for (int b = 0; b < a->batch; ++b) {  // serial over batch rows, like the reference's in-kernel `for b` (:1011)
+            q.x = a->vec + (size_t)b * a->in_features;
+            q.out = a->mul + (size_t)b * a->out_features;
+            rc = launch2(a, 0, false, q, static_cast<cudaStream_t>(stream));
+            if (rc) return rc;
+        }
+        return SQLLM_OK;
+    }
     Plan pl;
     rc = make_plan(a->bits, a->in_features, a->out_features, hyb ? a->topX : 0, a->rows != nullptr, false, pl);
     if (rc) return rc;
@@ -1629,6 +1853,16 @@ int sqllm_lutgemv_fused(const sqllm_lutgemv_args *a, const void *x, int x_is_hal
     if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15)) return fail(SQLLM_EINVAL, "y and bias must be 16-byte aligned");
     const bool hyb = a->full_rows && a->topX > 0;
     if (hyb && a->topX > MAX_TOPX_FUSED) return fail(SQLLM_EINVAL, "fused path supports topX <= %d", MAX_TOPX_FUSED);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    if (det_mode() == 0 && kernel_sel() == 2 && a->out_features >= STRIP) {
+        if (!workspace || workspace_bytes < WS_HEADER) return fail(SQLLM_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", (size_t)WS_HEADER, workspace_bytes);
+        v2::P2 q;
+        memset(&q, 0, sizeof(q));
+        q.ws_cnt = reinterpret_cast<int *>(ws);
+        q.ws_acc = reinterpret_cast<float *>(ws + WS_ACC_OFF);
+        q.x = x; q.out = y; q.y_is_half = y_is_half; q.bias = bias;
+        return launch2(a, x_is_half ? (lut_mode() == 1 ? 2 : 1) : 0, true, q, static_cast<cudaStream_t>(stream));
+    }
     Plan pl;
     rc = make_plan(a->bits, a->in_features, a->out_features, hyb ? a->topX : 0, a->rows != nullptr, true, pl);
     if (rc) return rc;
@@ -1636,7 +1870,6 @@ int sqllm_lutgemv_fused(const sqllm_lutgemv_args *a, const void *x, int x_is_hal
         return fail(SQLLM_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.ws_bytes, workspace_bytes);
     Params p;
     memset(&p, 0, sizeof(p));
-    unsigned char *ws = static_cast<unsigned char *>(workspace);
     p.ws_cnt = reinterpret_cast<int *>(ws + pl.ws_cnt_off);
     p.ws_hyb_cnt = reinterpret_cast<int *>(ws + pl.ws_hybcnt_off);
     p.ws_hyb = reinterpret_cast<float *>(ws + pl.ws_hyb_off);
@@ -1666,6 +1899,19 @@ int sqllm_lutgemv_fused_exchange(const sqllm_lutgemv_args *a, const void *x, int
     if ((xc->out_features_full * (y_is_half ? 2 : 4)) % 16 || (w * (y_is_half ? 2 : 4)) % 8) return fail(SQLLM_EINVAL, "vector sizes must keep 8/16-byte store alignment");
     const bool hyb = a->full_rows && a->topX > 0;
     if (hyb && a->topX > MAX_TOPX_FUSED) return fail(SQLLM_EINVAL, "fused path supports topX <= %d", MAX_TOPX_FUSED);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    if (kernel_sel() == 2 && a->out_features >= STRIP) {
+        if (!workspace || workspace_bytes < WS_HEADER) return fail(SQLLM_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", (size_t)WS_HEADER, workspace_bytes);
+        v2::P2 q;
+        memset(&q, 0, sizeof(q));
+        q.ws_cnt = reinterpret_cast<int *>(ws);
+        q.ws_acc = reinterpret_cast<float *>(ws + WS_ACC_OFF);
+        q.x = x; q.out = nullptr; q.y_is_half = y_is_half; q.bias = bias;
+        q.xw_world = xc->world; q.xw_rank = xc->rank; q.xw_members = xc->members; q.xw_nfull = xc->out_features_full;
+        q.xw_base = reinterpret_cast<const unsigned long long *>(xc->peer_base);
+        q.xw_out_off = xc->out_offset; q.xw_flag_off = xc->flag_offset; q.xw_state_off = xc->state_offset; q.xw_err_off = xc->error_offset;
+        return launch2(a, x_is_half ? (lut_mode() == 1 ? 2 : 1) : 0, true, q, static_cast<cudaStream_t>(stream));
+    }
     Plan pl;
     rc = make_plan(a->bits, a->in_features, a->out_features, hyb ? a->topX : 0, a->rows != nullptr, true, pl);
     if (rc) return rc;
@@ -1673,7 +1919,6 @@ int sqllm_lutgemv_fused_exchange(const sqllm_lutgemv_args *a, const void *x, int
         return fail(SQLLM_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.ws_bytes, workspace_bytes);
     Params p;
     memset(&p, 0, sizeof(p));
-    unsigned char *ws = static_cast<unsigned char *>(workspace);
     p.ws_cnt = reinterpret_cast<int *>(ws + pl.ws_cnt_off);
     p.ws_hyb_cnt = reinterpret_cast<int *>(ws + pl.ws_hybcnt_off);
     p.ws_hyb = reinterpret_cast<float *>(ws + pl.ws_hyb_off);

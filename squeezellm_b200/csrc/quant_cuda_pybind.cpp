@@ -15,8 +15,11 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cuda_runtime.h>
+
 #include <map>
 #include <mutex>
+#include <string>
 
 #include "sqllm_b200.h"
 
@@ -288,5 +291,28 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("abi_version", []() { return sqllm_abi_version(); });
     m.def("set_deterministic", [](bool on) { sqllm_set_deterministic(on ? 1 : 0); },
           "fused path: True = bit-reproducible fixed-order reduction, False (default) = red.add accumulation");
+    m.def("set_lut_mode", [](const std::string &mode) {
+              TORCH_CHECK(mode == "exact" || mode == "fp16", "lut mode must be 'exact' or 'fp16' (got '", mode, "')");
+              sqllm_set_lut_mode(mode == "fp16" ? SQLLM_LUT_FP16_PAIR : SQLLM_LUT_EXACT);
+          },
+          "fused path: 'exact' (default) = fp32 codebook as stored; 'fp16' = centroids rounded to fp16, pair tables + fp16 x fp16 -> fp32 FMAs "
+          "(only taken for fp16 x)");
+    m.def("get_lut_mode", []() { return std::string(sqllm_get_lut_mode() == SQLLM_LUT_FP16_PAIR ? "fp16" : "exact"); });
+    m.def("workspace_error", []() {
+              // error word of the current stream's fused-path workspace on the current device (synchronises the stream)
+              int dev = 0;
+              C10_CUDA_CHECK(cudaGetDevice(&dev));
+              torch::Tensor ws;
+              {
+                  std::lock_guard<std::mutex> lock(g_ws_mutex);
+                  auto it = g_ws.find(std::make_pair(dev, cur_stream()));
+                  if (it == g_ws.end()) return false;
+                  ws = it->second;
+              }
+              const int rc = sqllm_workspace_error(ws.data_ptr(), cur_stream());
+              TORCH_CHECK(rc >= 0, "workspace_error: ", sqllm_last_error());
+              return rc == 1;
+          },
+          "True if a bounded in-kernel wait of the fused path ever timed out on this stream's workspace (results are then incomplete)");
     m.def("sm_count", []() { return sqllm_device_sm_count(); });
 }

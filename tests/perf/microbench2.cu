@@ -1,0 +1,247 @@
+// microbench2.cu - round-2 design probes on a B200 (standalone, no torch):
+//   pair    : the fp16 pair-table gather loop (one PRMT + one LDS.32 per TWO 4-bit weights, two mixed-precision
+//             fma.rn.f32.f16 = SASS FHFMA per pair) against the exact loop (one PRMT + LDS.32 per weight, FFMA2)
+//   fhfma   : issue rate of FHFMA alone (is it a full-rate FMA-pipe instruction?)
+//   stream  : LDG.128 stream with 32- / 64- / 128-column row segments (DRAM efficiency of narrow strips)
+//   cluster : how many SMs a cluster launch can use (cudaOccupancyMaxActiveClusters for sizes 2, 4, 8)
+// build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o microbench2 microbench2.cu
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_v4(uint32_t a) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void ffma2(uint64_t &acc, uint64_t a, uint64_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+// d += lo16(a)*lo16(b) ; d += hi16(a)*hi16(b)   (fp16 x fp16 -> fp32 accumulate: SASS FHFMA with .H0/.H1 operand selectors)
+__device__ __forceinline__ void fhfma_pair(float &acc, uint32_t a, uint32_t b) {
+    asm("{\n.reg .b16 al, ah, bl, bh;\nmov.b32 {al, ah}, %1;\nmov.b32 {bl, bh}, %2;\nfma.rn.f32.f16 %0, al, bl, %0;\nfma.rn.f32.f16 %0, ah, bh, %0;\n}"
+        : "+f"(acc) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void fhfma_pair2(float &acc0, float &acc1, uint32_t a, uint32_t b) {  // two chains
+    asm("{\n.reg .b16 al, ah, bl, bh;\nmov.b32 {al, ah}, %2;\nmov.b32 {bl, bh}, %3;\nfma.rn.f32.f16 %0, al, bl, %0;\nfma.rn.f32.f16 %1, ah, bh, %1;\n}"
+        : "+f"(acc0), "+f"(acc1) : "r"(a), "r"(b));
+}
+
+// MODE 0: exact   - per word 8 x (PRMT + LDS.32) + 4 FFMA2, x as 2 LDS.128 of fp32            (the round-1 loop)
+// MODE 1: pair16  - per word 4 x (PRMT + LDS.32) + 8 FHFMA,  x as 1 LDS.128 of 8 halves       (table [256][64 slots] half2 = 64 KB)
+// MODE 2: pair16 lookups only (no FMA)                                                          (LSU bound of the pair gather)
+// MODE 3: pair16 with cvt + FFMA2 instead of FHFMA (2 HADD2.F32 + FFMA2 per pair, x fp32)
+template <int MODE>
+__global__ void lookup_kernel(int iters, float *out) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t tb = (raw + 65535u) & ~65535u;  // 64 KB aligned table (pair modes need bits 8..15 free for the pair value)
+    unsigned char *sm = smem_raw + (tb - raw);
+    uint32_t *tab = (uint32_t *)sm;
+    const int nent = MODE == 0 ? 1024 : 16384;
+    for (int e = threadIdx.x; e < nent + 64; e += blockDim.x) tab[e] = MODE == 0 ? __float_as_uint(1.0f + (e & 15) * 0.001f) : 0x3C003C00u + (e & 7);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, i16 = lane & 15, jsel = lane >> 4;
+    uint32_t ls[4];
+    for (int t = 0; t < 4; ++t) ls[t] = (tb & 0xFFFF0000u) | ((((t ^ jsel) << 4) | i16) << 2);
+    const uint32_t segc = ((tb >> 8) & 0xF0u) * 0x01010101u;
+    const uint32_t xaddr = tb + (MODE == 0 ? 4096 : 65536);
+    uint64_t acc[4] = {0, 0, 0, 0};
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t w0 = threadIdx.x * 2654435761u + blockIdx.x, w1 = w0 * 31 + 7, w2 = w1 * 31 + 7, w3 = w2 * 31 + 7;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t w[4] = {w0, w1, w2, w3};
+        if (MODE == 0) {
+            const float4 xa = lds_v4(xaddr), xb = lds_v4(xaddr + 16);
+            const uint64_t x01 = pack2(xa.x, xa.y), x23 = pack2(xa.z, xa.w), x45 = pack2(xb.x, xb.y), x67 = pack2(xb.z, xb.w);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t E = (w[t] & 0x0F0F0F0Fu) | segc;
+                const uint32_t O = ((w[t] >> 4) & 0x0F0F0F0Fu) | segc;
+                const float e0 = lds_f32(__byte_perm(E, ls[t], 0x7604)), o0 = lds_f32(__byte_perm(O, ls[t], 0x7604));
+                const float e1 = lds_f32(__byte_perm(E, ls[t], 0x7614)), o1 = lds_f32(__byte_perm(O, ls[t], 0x7614));
+                const float e2 = lds_f32(__byte_perm(E, ls[t], 0x7624)), o2 = lds_f32(__byte_perm(O, ls[t], 0x7624));
+                const float e3 = lds_f32(__byte_perm(E, ls[t], 0x7634)), o3 = lds_f32(__byte_perm(O, ls[t], 0x7634));
+                ffma2(acc[t], pack2(e0, o0), x01); ffma2(acc[t], pack2(e1, o1), x23);
+                ffma2(acc[t], pack2(e2, o2), x45); ffma2(acc[t], pack2(e3, o3), x67);
+            }
+        } else if (MODE == 3) {
+            const float4 xa = lds_v4(xaddr), xb = lds_v4(xaddr + 16);
+            const uint64_t x01 = pack2(xa.x, xa.y), x23 = pack2(xa.z, xa.w), x45 = pack2(xb.x, xb.y), x67 = pack2(xb.z, xb.w);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t p0 = lds_u32(__byte_perm(w[t], ls[t], 0x7604)), p1 = lds_u32(__byte_perm(w[t], ls[t], 0x7614));
+                const uint32_t p2 = lds_u32(__byte_perm(w[t], ls[t], 0x7624)), p3 = lds_u32(__byte_perm(w[t], ls[t], 0x7634));
+                const float2 a0 = __half22float2(*reinterpret_cast<const __half2 *>(&p0)), a1 = __half22float2(*reinterpret_cast<const __half2 *>(&p1));
+                const float2 a2 = __half22float2(*reinterpret_cast<const __half2 *>(&p2)), a3 = __half22float2(*reinterpret_cast<const __half2 *>(&p3));
+                ffma2(acc[t], pack2(a0.x, a0.y), x01); ffma2(acc[t], pack2(a1.x, a1.y), x23);
+                ffma2(acc[t], pack2(a2.x, a2.y), x45); ffma2(acc[t], pack2(a3.x, a3.y), x67);
+            }
+        } else {
+            const uint4 xh = lds_u4(xaddr);  // 8 halves: (x0,x1) (x2,x3) (x4,x5) (x6,x7)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t p0 = lds_u32(__byte_perm(w[t], ls[t], 0x7604)), p1 = lds_u32(__byte_perm(w[t], ls[t], 0x7614));
+                const uint32_t p2 = lds_u32(__byte_perm(w[t], ls[t], 0x7624)), p3 = lds_u32(__byte_perm(w[t], ls[t], 0x7634));
+                if (MODE == 1) {
+                    fhfma_pair2(f[t], f[t + 4], p0, xh.x); fhfma_pair2(f[t], f[t + 4], p1, xh.y);
+                    fhfma_pair2(f[t], f[t + 4], p2, xh.z); fhfma_pair2(f[t], f[t + 4], p3, xh.w);
+                } else {
+                    f[t] += __uint_as_float(p0 ^ p1); f[t + 4] += __uint_as_float(p2 ^ p3);
+                }
+            }
+        }
+        w0 = w0 * 1664525u + 1013904223u; w1 = w1 * 1664525u + 1013904223u; w2 = w2 * 1664525u + 1013904223u; w3 = w3 * 1664525u + 1013904223u;
+    }
+    float s = 0;
+    for (int t = 0; t < 4; ++t) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[t])); s += lo + hi; }
+    for (int t = 0; t < 8; ++t) s += f[t];
+    if (s == 1234.5f) out[0] = s;
+}
+
+// FHFMA issue rate: 16 independent chains per thread, no memory
+template <int KIND>  // 0: FHFMA  1: FFMA  2: FFMA2
+__global__ void fma_kernel(int iters, float *out, uint32_t a0, uint32_t b0) {
+    float f[16];
+    uint64_t g[8];
+    for (int i = 0; i < 16; ++i) f[i] = (float)(threadIdx.x + i);
+    for (int i = 0; i < 8; ++i) g[i] = pack2(f[2 * i], f[2 * i + 1]);
+    uint32_t a = a0 + threadIdx.x, b = b0;
+    const float fa = __uint_as_float(a), fb = __uint_as_float(b);
+    const uint64_t pa = pack2(fa, fb), pb = pack2(fb, fa);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (KIND == 0) fhfma_pair2(f[2 * i], f[2 * i + 1], a, b);
+            else if (KIND == 1) { f[2 * i] = fmaf(fa, fb, f[2 * i]); f[2 * i + 1] = fmaf(fb, fa, f[2 * i + 1]); }
+            else ffma2(g[i], pa, pb);
+        }
+    }
+    float s = 0;
+    for (int i = 0; i < 16; ++i) s += f[i];
+    for (int i = 0; i < 8; ++i) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(g[i])); s += lo + hi; }
+    if (s == 1234.5f) out[0] = s;
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+template <int STRIPW, int U>
+__global__ void stream_kernel(const uint32_t *__restrict__ q, int rows, int N, int chunk, int T, uint32_t *out) {
+    constexpr int LPR = STRIPW / 4, RPW = 32 / LPR;
+    const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g0 = min(blockIdx.x * chunk, T), g1 = min(g0 + chunk, T);
+    const int li = lane % LPR, lj = lane / LPR;
+    uint32_t acc = 0;
+    uint4 buf[U];
+    auto addr = [&](int g) -> const uint32_t * {
+        const int strip = g / rows, r = g - strip * rows;
+        return q + (size_t)r * N + strip * STRIPW + 4 * li;
+    };
+    int g = g0 + warp * RPW + lj;
+    const int step = nw * RPW;
+#pragma unroll
+    for (int u = 0; u < U; ++u) buf[u] = (g + u * step < g1) ? ldg_stream(addr(g + u * step)) : make_uint4(0, 0, 0, 0);
+    for (; g < g1; g += U * step) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            acc ^= buf[u].x ^ buf[u].y ^ buf[u].z ^ buf[u].w;
+            const int gn = g + (u + U) * step;
+            buf[u] = (gn < g1) ? ldg_stream(addr(gn)) : make_uint4(0, 0, 0, 0);
+        }
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+__global__ void dummy_cluster_kernel(float *out) { if (out && threadIdx.x == 9999) out[0] = 1.f; }
+
+template <typename F>
+float time_ms(F f, int reps) {
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    f(); CK(cudaDeviceSynchronize());
+    float best = 1e9f;
+    for (int r = 0; r < reps; ++r) {
+        CK(cudaEventRecord(a)); f(); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best) best = ms;
+    }
+    return best;
+}
+
+template <int MODE>
+void run_lookup(const char *name, int sms, float *dout) {
+    CK(cudaFuncSetAttribute(lookup_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int smem = MODE == 0 ? 65536 + 8192 : 65536 + 65536 + 4096;
+    for (int occ : {1, 2}) for (int warps : {8, 14, 16, 24}) {
+        if (occ * smem > 227 * 1024 || occ * warps > 48) continue;
+        const int iters = 4000;
+        int real = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&real, lookup_kernel<MODE>, warps * 32, smem));
+        if (real < occ) continue;
+        float ms = time_ms([&] { lookup_kernel<MODE><<<sms * occ, warps * 32, smem>>>(iters, dout); }, 3);
+        const double weights = (double)sms * occ * warps * 32 * 32.0 * iters;
+        printf("%-28s CTAs/SM=%d warps/CTA=%2d : %6.2f Tweights/s = %5.1f weights/clk/SM @1.965 GHz\n", name, occ, warps, weights / ms / 1e9,
+               weights / ms / 1e3 / sms / 1.965e6);
+    }
+}
+
+int main() {
+    setvbuf(stdout, NULL, _IONBF, 0);
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    printf("SMs %d\n", sms);
+    float *dout; CK(cudaMalloc(&dout, 64));
+
+    run_lookup<0>("exact PRMT+LDS+FFMA2", sms, dout);
+    run_lookup<1>("pair16 PRMT+LDS+2xFHFMA", sms, dout);
+    run_lookup<2>("pair16 lookups only", sms, dout);
+    run_lookup<3>("pair16 cvt+FFMA2", sms, dout);
+
+    for (int warps : {4, 8, 16}) {
+        const int iters = 20000;
+        float m0 = time_ms([&] { fma_kernel<0><<<sms, warps * 32>>>(iters, dout, 0x3c003c00u, 0x3c003c00u); }, 3);
+        float m1 = time_ms([&] { fma_kernel<1><<<sms, warps * 32>>>(iters, dout, 0x3f800000u, 0x3f800000u); }, 3);
+        float m2 = time_ms([&] { fma_kernel<2><<<sms, warps * 32>>>(iters, dout, 0x3f800000u, 0x3f800000u); }, 3);
+        const double n = (double)sms * warps * 32 * iters;
+        printf("fma issue, %2d warps/SM: FHFMA %.1f  FFMA %.1f  FFMA2 %.1f  thread-instr/clk/SM (16 / 16 / 8 instr per iteration)\n", warps,
+               n * 16 / m0 / 1e3 / sms / 1.965e6, n * 16 / m1 / 1e3 / sms / 1.965e6, n * 8 / m2 / 1e3 / sms / 1.965e6);
+    }
+
+    {
+        const size_t bytes = 1ull << 30;
+        uint32_t *q; CK(cudaMalloc(&q, bytes)); CK(cudaMemset(q, 1, bytes));
+        uint32_t *o2; CK(cudaMalloc(&o2, 64));
+        for (int N : {4096, 11008}) {
+            const int rows = (int)(bytes / 4 / N) / 16 * 16;
+            const double mb = (double)rows * N * 4;
+            auto go = [&](auto kern, int stripw, int U, int occ, int threads) {
+                const int strips = N / stripw; const long long T = (long long)strips * rows;
+                const int G = sms * occ; const int chunk = (int)((T + G - 1) / G);
+                float ms = time_ms([&] { kern<<<G, threads>>>(q, rows, N, chunk, (int)T, o2); }, 3);
+                printf("stream N=%5d stripw=%3d U=%d CTAs/SM=%d warps=%2d : %.1f GB/s\n", N, stripw, U, occ, threads / 32, mb / ms / 1e6);
+            };
+            go(stream_kernel<32, 8>, 32, 8, 2, 512);
+            go(stream_kernel<64, 8>, 64, 8, 2, 512);
+            go(stream_kernel<128, 8>, 128, 8, 2, 512);
+            go(stream_kernel<32, 8>, 32, 8, 1, 512);
+            go(stream_kernel<64, 8>, 64, 8, 1, 512);
+        }
+    }
+
+    for (int cs : {2, 4, 8}) {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(sms / cs * cs); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 100 * 1024;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaFuncSetAttribute(dummy_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int ncl = -1;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, dummy_cluster_kernel, &cfg);
+        printf("cluster size %d, 512 threads, 100 KB smem: max active clusters %d (%s) -> %d CTAs on %d SMs\n", cs, ncl, cudaGetErrorString(e), ncl * cs, sms);
+    }
+    return 0;
+}

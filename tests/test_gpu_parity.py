@@ -25,6 +25,17 @@ SHAPES = [  # (bits, K, N, sparsity, topX, nonzero_full_rows, skew)
     (4, 4096, 11008, 0.0045, 10, True, False),
     (3, 11008, 4096, 0.0045, 0, False, True),
     (4, 5120, 5120, 0.0005, 10, True, False),   # 13B w4-s5
+    # BASELINE shapes that round 1 left out ("parity gaps")
+    (3, 4096, 11008, 0.0045, 10, False, False), # 7B w3-s45 gate/up
+    (4, 5120, 13824, 0.0005, 10, False, False), # 13B gate/up
+    (4, 13824, 5120, 0.0005, 10, False, False), # 13B down
+    (3, 8192, 8192, 0.0045, 10, False, False),  # 65B q/k/v/o
+    (3, 8192, 22016, 0.0045, 10, False, False), # 65B gate/up
+    (3, 22016, 8192, 0.0045, 10, True, False),  # 65B down
+    (3, 8192, 2752, 0.0045, 10, False, False),  # 65B gate/up, 1 of 8 column shards: 43 strips, not a multiple of 128
+    (3, 22016, 1024, 0.0045, 10, False, False), # 65B down, 1 of 8 column shards
+    (4, 4096, 22016, 0.0045, 10, False, False), # 7B gate+up stacked (fusion.py)
+    (4, 4096, 12288, 0.0045, 10, True, True),   # 7B q+k+v stacked, skewed outliers
 ]
 IDS = [f"w{b}-{k}x{n}-s{int(s*1e4)}-t{t}{'-nz' if z else ''}{'-skew' if sk else ''}" for b, k, n, s, t, z, sk in SHAPES]
 

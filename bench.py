@@ -13,7 +13,11 @@ lm_head and the KV cache are NOT part of the step (they are not on the path this
 `config`.  As `llama.py --include_sparse` always runs (llama.py:301-306), sparse layers use the hybrid symbol with
 topX=10 dense rows that are zero (a checkpoint without them, llama.py:182).
 
-  value  : tokens/s, device-timed, inputs resident in HBM, one CUDA-graph replay per step.
+  value  : tokens/s, device-timed, inputs resident in HBM, one CUDA-graph replay per step; --steps K steps per timed block,
+           5 blocks, the MEDIAN block is reported (ms_per_step = median block / K; all block times are in `blocks_ms`).
+  lut_fp16: the same measurement with the fp16 pair-table mode of the kernel (quant_cuda.set_lut_mode("fp16"), north_star's
+           "per-channel fp16 LUT"); the headline `value` always uses the exact fp32 codebook.  `--lut fp16` makes it the only run.
+  parity_check: outside the timed region, one sampled layer group per rank against the fp64 CPU oracle on the same buffers.
   e2e    : same metric through the public API (squeezellm_b200.runtime.GraphedDecodeStep over QuantLinearLUT.forward)
            with the token's activation coming from pinned host memory and the result read back every step.
   roofline: algorithmic bytes of all launches of the step / step time vs the measured HBM copy bandwidth.
@@ -115,71 +119,69 @@ def build_model(cfg, dev, rank, world, seed=0):
 
 
 def make_step(layers, world, peer=None):
-    """x [hidden] -> x' [hidden]: the 7 matvecs per decoder layer in model order (see module docstring)."""
-    if world == 1:
-        def step(x):
-            for L in layers:
-                L["q_proj"](x)
-                L["k_proj"](x)
-                v = L["v_proj"](x)
-                o = L["o_proj"](v)
-                g = L["gate_proj"](o)
-                L["up_proj"](o)
-                x = L["down_proj"](g)
-            return x
-        return step
-
-    import torch.distributed as dist
-    from squeezellm_b200.sharding import exchange_stacked
-    rank = dist.get_rank()
-    bufs = {}
+    """Returns (step, run_layer).  step: x [hidden] -> x' [hidden], the 7 matvecs per decoder layer in model order (see module
+    docstring).  run_layer(L, x) runs ONE decoder layer the same way and returns [(name, input, full-length output)] for the 7
+    matvecs - what parity_check compares with the oracle (at N > 1: after the exchange, i.e. the vectors the next matvec reads)."""
     QKV, GU = ("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")
+    if world == 1:
+        def run_layer(L, x):
+            q, k, v = L["q_proj"](x), L["k_proj"](x), L["v_proj"](x)
+            o = L["o_proj"](v)
+            g, u = L["gate_proj"](o), L["up_proj"](o)
+            d = L["down_proj"](g)
+            return [("q_proj", x, q), ("k_proj", x, k), ("v_proj", x, v), ("o_proj", v, o), ("gate_proj", o, g), ("up_proj", o, u), ("down_proj", g, d)]
+    else:
+        import torch.distributed as dist
+        from squeezellm_b200.sharding import exchange_stacked
+        rank = dist.get_rank()
+        bufs = {}
 
-    def group_layer(L, names):
-        g = L[names[0]]._sibling_group
-        return g[0].layer if g is not None else None
+        def group_layer(L, names):
+            g = L[names[0]]._sibling_group
+            return g[0].layer if g is not None else None
 
-    if peer is not None:
-        # the kernel's finishing CTAs store their slice into every rank's arena over NVLink and wait for the peers': no collective
-        def run(layer, x, slot, members):
-            return peer.forward(layer, x, slot, members, layer.outfeatures // members * world)
+        if peer is not None:
+            # the kernel's finishing CTAs store their slice into every rank's arena over NVLink and wait for the peers': no collective
+            def run(layer, x, slot, members):
+                return peer.forward(layer, x, slot, members, layer.outfeatures // members * world)
 
-        def stacked(L, names, x, slot):
-            layer = group_layer(L, names)
-            if layer is not None:
-                return run(layer, x, slot, len(names))
-            return [run(L[n], x, slot + n, 1)[0] for n in names]
+            def stacked(L, names, x, slot):
+                layer = group_layer(L, names)
+                if layer is not None:
+                    return run(layer, x, slot, len(names))
+                return [run(L[n], x, slot + n, 1)[0] for n in names]
 
-        def step(x):
-            for L in layers:
-                q, k, v = stacked(L, QKV, x, "qkv")
-                o = run(L["o_proj"], v, "o", 1)[0]
-                g, u = stacked(L, GU, o, "gu")
-                x = run(L["down_proj"], g, "d", 1)[0]
-            return x.clone()
-        return step
+            def single(L, name, x, slot):
+                return run(L[name], x, slot, 1)[0]
+        else:
+            def exchange(name, y, members):
+                """this rank's (stacked) column shard -> zero-padded full-length vectors -> ONE all-reduce (north_star)."""
+                w = y.shape[-1] // members
+                if name not in bufs:
+                    bufs[name] = torch.zeros((members, w * world), dtype=y.dtype, device=y.device)
+                return exchange_stacked(y, members, rank, world, out=bufs[name])
 
-    def exchange(name, y, members):
-        """this rank's (stacked) column shard -> zero-padded full-length vectors -> ONE all-reduce (north_star)."""
-        w = y.shape[-1] // members
-        if name not in bufs:
-            bufs[name] = torch.zeros((members, w * world), dtype=y.dtype, device=y.device)
-        return exchange_stacked(y, members, rank, world, out=bufs[name])
+            def stacked(L, names, x, slot):
+                layer = group_layer(L, names)
+                if layer is not None:  # q/k/v (gate/up) shards stacked: one launch, one all-reduce for all members
+                    return exchange(names[0], layer(x), len(names))
+                return [exchange(n, L[n](x), 1)[0] for n in names]
 
-    def stacked(L, names, x):
-        layer = group_layer(L, names)
-        if layer is not None:  # q/k/v (gate/up) shards stacked: one launch, one all-reduce for all members
-            return exchange(names[0], layer(x), len(names))
-        return [exchange(n, L[n](x), 1)[0] for n in names]
+            def single(L, name, x, slot):
+                return exchange(slot, L[name](x), 1)[0]
+
+        def run_layer(L, x):
+            q, k, v = stacked(L, QKV, x, "qkv")
+            o = single(L, "o_proj", v, "o")
+            g, u = stacked(L, GU, o, "gu")
+            d = single(L, "down_proj", g, "d")
+            return [("q_proj", x, q), ("k_proj", x, k), ("v_proj", x, v), ("o_proj", v, o), ("gate_proj", o, g), ("up_proj", o, u), ("down_proj", g, d)]
 
     def step(x):
         for L in layers:
-            q, k, v = stacked(L, QKV, x)
-            o = exchange("o", L["o_proj"](v), 1)[0]
-            g, u = stacked(L, GU, o)
-            x = exchange("d", L["down_proj"](g), 1)[0]
-        return x.clone()
-    return step
+            x = run_layer(L, x)[-1][2]
+        return x.clone() if world > 1 else x
+    return step, run_layer
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -287,20 +289,25 @@ def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
+    nthr = host_threads()  # physical cores of one NUMA node, affinity pinned: the 128-thread oversubscribed run of round 1 varied 8x
+    torch.set_num_threads(nthr)
     times, fused, thr = cpu_layer_sample(cfg, args.warmup + args.steps)
     t = times[args.warmup:]
-    per_tok = statistics.mean(t) * cfg["layers"]
+    layer_s = statistics.median(t)
+    per_tok = layer_s * cfg["layers"]
     val = 1.0 / per_tok
-    fused_val = 1.0 / (statistics.mean(fused[args.warmup:]) * cfg["layers"])
-    sample = f"1 of {cfg['layers']} decoder layers (7 matvecs) per step, fp16 dequant + torch.matmul + CSR + dense rows; x{cfg['layers']} extrapolated"
-    config = base_config(args, cfg)
-    config["note"] = "the reference has no CPU path; this arm is the CPU restatement north_star names (oracle/), all host threads"
+    fused_val = 1.0 / (statistics.median(fused[args.warmup:]) * cfg["layers"])
+    sample = (f"each step = 1 of {cfg['layers']} decoder layers (7 matvecs: fp16 dequant + torch.matmul + CSR + dense rows), median of {len(t)} steps; "
+              f"tokens/s = 1 / (layer time x {cfg['layers']}); ms_per_step is the MEASURED layer time")
+    config = {**base_config(args, cfg), "launches_per_step": 0, "sibling_fusion": "n/a (CPU)", "l2": "n/a (CPU)", "parallelism": "host threads",
+              "exchange": "none", "launch": "n/a (CPU)", "lut": "exact", "timing": f"median of {len(t)} steps", "layers_timed": 1}
     out = {"metric": metric_name(args.workload), "value": val, "unit": "tokens/s", "impl": "reference",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_tok * 1e3, "higher_is_better": True,
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": layer_s * 1e3, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f16 weights x f16 activations (torch CPU matmul)", "data": "synthetic",
            "config": config,
-           "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+           "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": nthr, "kind": "port", "sample": sample,
+                            "note": "the reference has no CPU path; this arm is the CPU restatement north_star names (oracle/), pinned to the physical cores of one NUMA node",
+                            "layer_ms": layer_s * 1e3, "layers_per_token": cfg["layers"],
                             "fused_lookup_gemv_port_tokens_per_s": fused_val, "fused_port_threads": thr, "host_cpus": os.cpu_count(),
                             "matmul_only_on_predequantized_fp16_tokens_per_s": 1.0 / (min(cpu_layer_sample.matmul_only) * cfg["layers"])},
            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -321,6 +328,9 @@ def main():
                     help="N>1: how column shards are reassembled - p2p: stores into every rank's symmetric arena from inside the GEMV "
                          "kernel (falls back to nccl if symmetric memory is unavailable or the self-check fails); nccl: one all-reduce per launch")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinearLUT (no q/k/v and gate/up sibling stacking)")
+    ap.add_argument("--lut", default="both", choices=["both", "exact", "fp16"],
+                    help="codebook precision: exact = fp32 as stored (headline), fp16 = pair tables; both = headline exact + a lut_fp16 object")
+    ap.add_argument("--blocks", type=int, default=5, help="timed blocks of --steps steps each; the median block is reported")
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload])
     if args.layers:
@@ -368,17 +378,19 @@ def main():
     exchange_used, peer_used = "none", None
     if world > 1:
         import torch.distributed as dist
-        step_nccl = make_step(layers, world)
+        step_nccl, run_layer_nccl = make_step(layers, world)
+        run_layer = run_layer_nccl
         step, exchange_used = step_nccl, "nccl all-reduce per launch"
         if args.exchange == "p2p":
             why, ok, step_p2p = None, 0.0, None
             try:
                 from squeezellm_b200.sharding import PeerExchange
                 peer = PeerExchange(rank, world, dev)
-                step_p2p = make_step(layers, world, peer)
+                step_p2p, run_layer_p2p = make_step(layers, world, peer)
                 xs = torch.randn(cfg["hidden"], device=dev, generator=torch.Generator(device=dev).manual_seed(7)).half()
                 a, b = step_p2p(xs).float(), step_nccl(xs).float()
                 torch.cuda.synchronize()
+                # start-up smoke check only (does the exchange deliver at all?); the parity statement is parity_check, against the fp64 oracle
                 good = (not peer.error()) and bool(torch.isfinite(a).all()) and bool((a - b).abs().max() <= 2e-2 * b.abs().max().clamp_min(1e-3))
                 ok = 1.0 if good else 0.0
                 if not good:
@@ -389,10 +401,11 @@ def main():
             dist.all_reduce(vote, op=dist.ReduceOp.MIN)  # every rank takes the same decision
             if vote.item() == 1.0:
                 step, exchange_used, peer_used = step_p2p, "in-kernel stores to every rank's symmetric arena over NVLink (no collective)", peer
+                run_layer = run_layer_p2p
             elif why or rank == 0:
                 print(f"[bench] rank {rank}: p2p exchange not used ({why or 'another rank declined'}); falling back to NCCL", file=sys.stderr)
     else:
-        step = make_step(layers, world)
+        step, run_layer = make_step(layers, world)
     x0 = torch.randn(cfg["hidden"], device=dev).half()
 
     def barrier():
@@ -401,72 +414,97 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from squeezellm_b200.quant import quant_cuda
     from squeezellm_b200.runtime import GraphedDecodeStep
-    graphed = True
-    try:
-        runner = GraphedDecodeStep(step, x0, warmup=3)
-    except Exception as e:  # e.g. NCCL refusing capture: fall back to eager launches, and say so
-        if world == 1:
-            raise
-        graphed, runner = False, None
-        print(f"[bench] graph capture failed on rank {rank}: {e}; timing eager", file=sys.stderr)
-        torch.cuda.synchronize()
-
-    def one_step():
-        if graphed:
-            runner.replay()
-        else:
-            step(x0)
-
-    # ---- device-resident timing --------------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        one_step()
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        one_step()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- end to end from host memory through the public API ---------------------------------------------------
     xh = torch.randn(cfg["hidden"]).half().pin_memory()
-    e2e_ms = None
-    if graphed:
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+
+    def measure(lut_mode, sample_clocks):
+        """One full measurement (device-resident blocks, then end to end from host memory) with the given codebook mode.
+        The mode is baked into the graph at capture time (the kernel variant is chosen per launch)."""
+        quant_cuda.set_lut_mode(lut_mode)
+        graphed = True
+        try:
+            runner = GraphedDecodeStep(step, x0, warmup=3)
+        except Exception as e:  # e.g. NCCL refusing capture: fall back to eager launches, and say so
+            if world == 1:
+                raise
+            graphed, runner = False, None
+            print(f"[bench] graph capture failed on rank {rank}: {e}; timing eager", file=sys.stderr)
+            torch.cuda.synchronize()
+
+        def one_step():
+            if graphed:
+                runner.replay()
+            else:
+                step(x0)
+
         for _ in range(args.warmup):
-            runner(xh)
+            one_step()
         barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            runner(xh)
-        ev1.record()
+        if sample_clocks and rank == 0:
+            sampler.start()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.blocks + 1)]
+        evs[0].record()
+        for b in range(args.blocks):
+            for _ in range(args.steps):
+                one_step()
+            evs[b + 1].record()
+        barrier()
+        blocks = [evs[b].elapsed_time(evs[b + 1]) for b in range(args.blocks)]
+        clocks = sampler.stop() if (sample_clocks and rank == 0) else None
+        # end to end from host memory through the public API
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if graphed:
+            for _ in range(args.warmup):
+                runner(xh)
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                runner(xh)
+            ev1.record()
+        else:
+            yh = torch.empty(cfg["hidden"], dtype=torch.float16).pin_memory()
+            for _ in range(args.warmup):
+                yh.copy_(step(xh.to(dev, non_blocking=True)))
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                yh.copy_(step(xh.to(dev, non_blocking=True)))
+            ev1.record()
         barrier()
         e2e_ms = ev0.elapsed_time(ev1)
-    else:
-        yh = torch.empty(cfg["hidden"], dtype=torch.float16).pin_memory()
-        for _ in range(args.warmup):
-            yh.copy_(step(xh.to(dev, non_blocking=True)))
-        barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            yh.copy_(step(xh.to(dev, non_blocking=True)))
-        ev1.record()
-        barrier()
-        e2e_ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor(blocks + [e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every block: max over ranks
+            blocks, e2e_ms = t.tolist()[:-1], t.tolist()[-1]
+        ms = statistics.median(blocks)
+        quant_cuda.set_lut_mode("exact")
+        return {"ms_step": ms / args.steps, "e2e_ms_step": e2e_ms / args.steps, "blocks_ms": [round(b, 4) for b in blocks],
+                "graphed": graphed, "clocks": clocks}
+
+    head_mode = "fp16" if args.lut == "fp16" else "exact"
+    main_run = measure(head_mode, True)
+    extra_run = measure("fp16", False) if args.lut == "both" else None
+
+    # ---- parity: one sampled layer group per rank against the fp64 oracle on the same buffers (outside every timed region) ----------
+    parity = parity_check(layers, run_layer, cfg, rank, world, dev, quant_cuda)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([parity["max_rel_err"], parity["fp16_max_norm_err"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity["max_rel_err"], parity["fp16_max_norm_err"] = t.tolist()
+        parity["ranks"] = world
 
     if peer_used is not None and peer_used.error():  # a bounded in-kernel wait gave up: the numbers of this run are not valid
         exchange_used += " - ERROR: a peer wait timed out during this run"
         print(f"[bench] rank {rank}: exchange error word is set", file=sys.stderr)
+    if quant_cuda.workspace_error():
+        print(f"[bench] rank {rank}: the fused-path workspace error word is set (a bounded in-kernel wait timed out)", file=sys.stderr)
+        parity["workspace_error"] = True
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = t.tolist()
         tot = torch.tensor([float(nbytes)], device=dev, dtype=torch.float64)
         dist.all_reduce(tot)
         nbytes_all = tot.item()
@@ -477,45 +515,139 @@ def main():
         leave(world)
         return
 
-    ms_step = ms / args.steps
+    ms_step = main_run["ms_step"]
     tok_s = 1e3 / ms_step
-    e2e_tok_s = 1e3 / (e2e_ms / args.steps)
+    e2e_tok_s = 1e3 / main_run["e2e_ms_step"]
+    graphed = main_run["graphed"]
     peak, peak_src = peaks()
     achieved = nbytes / (ms_step * 1e-3) / 1e9  # per GPU: this rank's bytes over the step time
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-    except Exception:
-        pass
+    if world == 1:  # measured with ncu on the default single-GPU command (profiles/); not meaningful for column shards
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        except Exception:
+            pass
+    kern = f"lutgemv2_kernel<{cfg['bits']}, {'fp16 pair table' if head_mode == 'fp16' else 'exact fp32 table'}, fused>"
     out = {
         "metric": metric_name(args.workload),
         "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 accumulate (fp32 LUT x fp16->fp32 activations, fp16 outputs)", "data": "synthetic",
+        "dtype": ("f32 accumulate (fp16-rounded LUT x fp16 activations, exact products, fp16 outputs)" if head_mode == "fp16" else
+                  "f32 accumulate (fp32 LUT x fp16->fp32 activations, fp16 outputs)"), "data": "synthetic",
         "config": {**base_config(args, cfg), "launches_per_step": nlaunch,
                    "sibling_fusion": "q/k/v and gate/up stacked (squeezellm_b200.fusion)" if nlaunch != nmat else "off",
                    "l2": f"{nbytes_all / 1e9:.2f} GB of distinct weights per step >> 126 MB L2 (inputs larger than L2)",
                    "parallelism": "single GPU" if world == 1 else f"column-sharded x{world}, {nlaunch} launches per step", "exchange": exchange_used,
-                   "launch": "one CUDA-graph replay per step" if graphed else "eager launches (graph capture unavailable)"},
+                   "launch": "one CUDA-graph replay per step" if graphed else "eager launches (graph capture unavailable)",
+                   "lut": head_mode, "timing": f"median of {args.blocks} blocks of {args.steps} steps", "layers_timed": cfg["layers"]},
+        "blocks_ms": main_run["blocks_ms"],
         "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": cfg["hidden"] * 2, "d2h_bytes_per_step": cfg["hidden"] * 2,
                 "api": "squeezellm_b200.runtime.GraphedDecodeStep over QuantLinearLUT.forward" if graphed else "QuantLinearLUT.forward eager"},
         "gpu_launches": nlaunch * args.steps,
-        "clocks": clocks,
+        "clocks": main_run["clocks"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "kernel": f"lutgemv_kernel<{cfg['bits']},fused>",
+                     "peak_source": peak_src, "kernel": kern,
                      "algorithmic_bytes_per_step_per_gpu": nbytes, "frac_of_nominal_8000": achieved / 8000.0},
+        "parity_check": parity,
     }
+    if extra_run is not None:
+        a2 = nbytes / (extra_run["ms_step"] * 1e-3) / 1e9
+        out["lut_fp16"] = {"value": 1e3 / extra_run["ms_step"], "unit": "tokens/s", "ms_per_step": extra_run["ms_step"],
+                           "e2e": 1e3 / extra_run["e2e_ms_step"], "blocks_ms": extra_run["blocks_ms"],
+                           "roofline_frac": a2 / peak, "achieved_GBps": a2,
+                           "note": "same graph with the kernel's fp16 pair-table mode (centroids rounded to fp16, fp16 x fp16 -> fp32 FMAs); "
+                                   "max-norm error vs the fp64 oracle in parity_check.fp16_max_norm_err"}
     if not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(host_threads())
         times, fused, thr = cpu_layer_sample(cfg, 2)
         per_tok = min(times) * cfg["layers"]
         out["cpu_baseline"] = {"value": 1.0 / per_tok, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"1 of {cfg['layers']} decoder layers (7 matvecs), best of 2, fp16 dequant + torch.matmul (+CSR, dense rows), x{cfg['layers']}",
+                               "layer_ms": min(times) * 1e3,
                                "fused_lookup_gemv_port_tokens_per_s": 1.0 / (min(fused) * cfg["layers"]), "fused_port_threads": thr,
                                "matmul_only_on_predequantized_fp16_tokens_per_s": 1.0 / (min(cpu_layer_sample.matmul_only) * cfg["layers"]),
                                "host_cpus": os.cpu_count()}
     print(json.dumps(out), flush=True)
     leave(world)
+
+
+def parity_check(layers, run_layer, cfg, rank, world, dev, quant_cuda):
+    """One sampled decoder layer (the same on every rank, so that the exchange is part of what is checked): its 7 matvecs run exactly as
+    in the timed step (run_layer: same module objects, sibling stacking, the exchange at N > 1) and every full-length output vector
+    is compared with the fp64 oracle evaluated on the same buffers and the same fp16 inputs.  At N > 1 each rank evaluates the
+    oracle on its own column shard and the slices are all-gathered, so every rank checks every rank's columns as delivered to it.
+    max_rel_err: exact codebook, the strict per-element metric of tests/util.py (floor 1 % of max|y|), tolerance 1e-3 (north_star).
+    fp16_max_norm_err: fp16 pair-table mode, max|y - o| / max|o| (tests/test_lut_fp16.py says why that mode is stated in the max norm)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle as orc
+    li = len(layers) // 2
+    L = layers[li]
+
+    def rel_err(a, b):
+        den = np.maximum(np.abs(b), 1e-2 * max(np.abs(b).max(), 1e-30))
+        return float((np.abs(a - b) / den).max())
+
+    def to_oracle(m):
+        d = dict(bits=m.bits, infeatures=m.infeatures, outfeatures=m.outfeatures, bias=None)
+        for k in ("qweight", "lookup_table", "rows", "cols", "vals", "full_rows", "full_row_indices"):
+            d[k] = getattr(m, k).detach().cpu().numpy() if hasattr(m, k) and getattr(m, k) is not None else None
+        return d
+
+    x = torch.randn(cfg["hidden"], device=dev, generator=torch.Generator(device=dev).manual_seed(4321)).half()  # same on every rank
+    worst = {"exact": 0.0, "fp16": 0.0}
+    for mode in ("exact", "fp16"):
+        quant_cuda.set_lut_mode(mode)
+        outs = run_layer(L, x)
+        torch.cuda.synchronize()
+        for name, xin, y in outs:
+            want = orc.forward_f64(to_oracle(L[name]), xin.float().cpu().numpy().reshape(1, -1)).reshape(-1)  # this rank's columns
+            if world > 1:
+                import torch.distributed as dist
+                parts = [torch.empty(want.shape[0], dtype=torch.float64, device=dev) for _ in range(world)]
+                dist.all_gather(parts, torch.from_numpy(want).to(dev))
+                want = torch.cat(parts).cpu().numpy()
+            got = y.float().cpu().numpy().reshape(-1)
+            if mode == "exact":
+                worst[mode] = max(worst[mode], rel_err(got, want))
+            else:
+                worst[mode] = max(worst[mode], float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)))
+    quant_cuda.set_lut_mode("exact")
+    return {"max_rel_err": worst["exact"], "tol": 1e-3, "fp16_max_norm_err": worst["fp16"], "fp16_tol": 1e-3,
+            "metric": "exact: max_i |y_i - o_i| / max(|o_i|, 1e-2 max|o|); fp16: max|y - o| / max|o|; o = fp64 oracle, y = fp16 output as the next matvec reads it",
+            "sample": f"decoder layer {li} of {len(layers)}, all 7 matvecs, run exactly as in the timed step" + (", after the exchange" if world > 1 else ""),
+            "ok": bool(worst["exact"] <= 1e-3 and worst["fp16"] <= 1e-3)}
+
+
+def host_threads():
+    """Threads for the CPU arm: the physical cores of ONE NUMA node (hyper-threads and the second socket only add noise here)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except Exception:
+        cpus = list(range(os.cpu_count() or 1))
+    node0 = set()
+    try:
+        for part in open("/sys/devices/system/node/node0/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            node0.update(range(int(a), int(b or a) + 1))
+    except Exception:
+        node0 = set(cpus)
+    phys = {}
+    for c in cpus:
+        if c not in node0:
+            continue
+        try:
+            core = open(f"/sys/devices/system/cpu/cpu{c}/topology/core_id").read().strip()
+        except Exception:
+            core = str(c)
+        phys.setdefault(core, c)
+    chosen = sorted(phys.values()) or cpus
+    try:
+        os.sched_setaffinity(0, chosen)
+    except Exception:
+        pass
+    os.environ["OMP_NUM_THREADS"] = str(len(chosen))
+    return len(chosen)
 
 
 if __name__ == "__main__":

@@ -592,19 +592,26 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             if (s + 1 < nseg) lut_prefetch<BITS>(p, lutbuf, s0 + s + 1, bt);  // next strip's rows: long there when they are needed
         }
         if (nseg <= 2) named_bar_sync(2, NCT + (NBW + NSPW) * 32);
-        for (int s = max(0, nseg - 2); s < nseg; ++s) {  // the last two segments
-            mbar_wait(bar_u32 + 272 + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
-            flush(s);
-        }
-        TRACE(8, bt == 0);
-        if constexpr (FUSED) {
-            // ---- finish the strips this CTA owns (those that start in its range): wait for the other contributors' announcements - dense
-            //      CTAs holding a later part, every CTA whose CSR rows touch the strip, the hc dense-row CTAs if a dense-row channel
-            //      lies in it - then y = accumulator (+ bias), accumulator and flag back to zero.  No grid-wide step: a CTA leaves as
-            //      soon as its own strips are complete.  Waits are bounded (2 s, then the workspace error word is set).
+        if constexpr (!FUSED) {
+            for (int s = max(0, nseg - 2); s < nseg; ++s) {  // the last two segments
+                mbar_wait(bar_u32 + 272 + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
+                flush(s);
+            }
+        } else {
+            // ---- finish the strips this CTA owns (those that start in its range).  Every table is built, so the builders have time: while
+            //      the consumers are still in the last segment they wait for the other contributors' announcements - dense CTAs holding a
+            //      later part, every CTA whose CSR rows touch the strip, the hc dense-row CTAs if a dense-row channel lies in it - and
+            //      fetch the accumulator.  What is left for the very end is y = accumulator + own last strip (+ bias): no round trip to
+            //      L2 after the last weight, no grid-wide step; a CTA leaves as soon as its own strips are complete.
+            //      Waits are bounded (2 s, then the workspace error word is set).
+            if (nseg >= 2) {
+                mbar_wait(bar_u32 + 272 + 8 * ((nseg - 2) & 1), (uint32_t)(((nseg - 2) >> 1) & 1));
+                flush(nseg - 2);
+            }
             const long long cb0 = (long long)blockIdx.x * p.chunk, cb1 = min((long long)p.T, cb0 + p.chunk);
-            const int so0 = (int)((cb0 + R - 1) / R), so1 = (int)((cb1 + R - 1) / R);
-            for (int i = bt; i < so1 - so0; i += NBT) {
+            const int so0 = (int)((cb0 + R - 1) / R), so1 = (int)((cb1 + R - 1) / R), nown = so1 - so0;
+            const bool last_owned = nseg >= 2 || r0 == 0;  // the last segment's strip starts in this CTA's range (it is strip so1 - 1)
+            for (int i = bt; i < nown; i += NBT) {
                 const int strip = so0 + i;
                 int expect = (int)((((long long)strip + 1) * R - 1) / p.chunk) - (int)blockIdx.x;  // dense CTAs after this one
                 if (p.rows) {
@@ -633,37 +640,58 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
                     flags[strip] = 0;
                 }
             }
-            named_bar_sync(3, NBT);  // every owned strip is complete (acquire above + barrier: visible to all 64 threads)
+            named_bar_sync(3, NBT);  // the others' contributions to every owned strip are complete (acquire above + barrier)
             const int w = p.xw_world ? N / p.xw_members : 0;
-            for (int i0 = 0; i0 < so1 - so0; i0 += 4) {
+            auto store_y = [&](int col, float yv) {
+                if (p.bias) yv += __ldg(p.bias + col);
+                if (p.xw_world == 0) {
+                    if (p.y_is_half) reinterpret_cast<__half *>(p.out)[col] = __float2half_rn(yv);
+                    else reinterpret_cast<float *>(p.out)[col] = yv;
+                } else {
+                    // local column col of the stacked shard = column j of member m; it lands at [m][rank*w + j] of the
+                    // [members][n_full] vector in EVERY rank's arena
+                    const int mm = col / w, j = col - mm * w;
+                    const unsigned long long e = (unsigned long long)mm * p.xw_nfull + (unsigned long long)p.xw_rank * w + j;
+                    for (int pr = 0; pr < p.xw_world; ++pr) {
+                        unsigned char *dst = reinterpret_cast<unsigned char *>(__ldg(p.xw_base + pr) + p.xw_out_off);
+                        if (p.y_is_half) *reinterpret_cast<__half *>(dst + 2 * e) = __float2half_rn(yv);
+                        else *reinterpret_cast<float *>(dst + 4 * e) = yv;
+                    }
+                }
+            };
+            // strips whose own part is already in the accumulator: all owned ones but (if owned) the last segment's
+            const int nearly = last_owned ? nown - 1 : nown;
+            for (int i0 = 0; i0 < nearly; i0 += 4) {
                 float vv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int col = (so0 + i0 + u) * STRIP + bt;
-                    vv[u] = (i0 + u < so1 - so0 && col < N) ? __ldcg(p.ws_acc + col) : 0.f;
+                    vv[u] = (i0 + u < nearly && col < N) ? __ldcg(p.ws_acc + col) : 0.f;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int col = (so0 + i0 + u) * STRIP + bt;
-                    if (i0 + u < so1 - so0 && col < N) {
+                    if (i0 + u < nearly && col < N) {
                         p.ws_acc[col] = 0.f;
-                        float yv = vv[u];
-                        if (p.bias) yv += __ldg(p.bias + col);
-                        if (p.xw_world == 0) {
-                            if (p.y_is_half) reinterpret_cast<__half *>(p.out)[col] = __float2half_rn(yv);
-                            else reinterpret_cast<float *>(p.out)[col] = yv;
-                        } else {
-                            // local column col of the stacked shard = column j of member m; it lands at [m][rank*w + j] of the
-                            // [members][n_full] vector in EVERY rank's arena
-                            const int mm = col / w, j = col - mm * w;
-                            const unsigned long long e = (unsigned long long)mm * p.xw_nfull + (unsigned long long)p.xw_rank * w + j;
-                            for (int pr = 0; pr < p.xw_world; ++pr) {
-                                unsigned char *dst = reinterpret_cast<unsigned char *>(__ldg(p.xw_base + pr) + p.xw_out_off);
-                                if (p.y_is_half) *reinterpret_cast<__half *>(dst + 2 * e) = __float2half_rn(yv);
-                                else *reinterpret_cast<float *>(dst + 4 * e) = yv;
-                            }
-                        }
+                        store_y(col, vv[u]);
                     }
+                }
+            }
+            float pre = 0.f;
+            const int lcol = (s0 + nseg - 1) * STRIP + bt;
+            if (last_owned && nseg > 0 && lcol < N) {
+                pre = __ldcg(p.ws_acc + lcol);   // what the others added to the last strip; our own part never goes through memory
+                p.ws_acc[lcol] = 0.f;
+            }
+            TRACE(8, bt == 0);
+            if (nseg > 0) {
+                const int s = nseg - 1;
+                mbar_wait(bar_u32 + 272 + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
+                if (last_owned) {
+                    const float own = lds_f32(sacc + 4 * ((s & 1) * STRIP + bt));
+                    if (lcol < N) store_y(lcol, pre + own);
+                } else {
+                    flush(s);  // a CTA that lies wholly inside a strip started by another one: contribute and announce
                 }
             }
             if (p.xw_world) {
@@ -673,7 +701,7 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
                 named_bar_sync(3, NBT);
                 if (bt == 0) {
                     const unsigned long long self = __ldg(p.xw_base + p.xw_rank);
-                    if (so1 > so0) {
+                    if (nown > 0) {
                         __threadfence_system();
                         for (int pr = 0; pr < p.xw_world; ++pr)
                             atomicAdd_system(reinterpret_cast<unsigned long long *>(__ldg(p.xw_base + pr) + p.xw_flag_off), 1ull);

@@ -20,6 +20,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "sqllm_b200.h"
 
@@ -143,8 +144,14 @@ void hybrid(torch::Tensor rows, torch::Tensor cols, torch::Tensor mat, torch::Te
 }
 
 // ---- fused module path ------------------------------------------------------------------------
+// Workspace of the fused path: one per (device, stream), allocated on first use (so: before any graph capture on that stream -
+// GraphedDecodeStep warms up for exactly this reason), at least 8 MB - every supported shape fits, it is never regrown in
+// practice; if it ever is, the old one is kept alive for graphs that captured its address.  A workspace serialises the launches
+// that use it: graphs captured on the SAME stream must not be replayed concurrently on different streams (they share it);
+// capture them on different streams if they have to overlap.
 std::mutex g_ws_mutex;
 std::map<std::pair<int, void *>, torch::Tensor> g_ws;  // (device, stream) -> zero-initialised workspace
+std::vector<torch::Tensor> g_ws_retired;               // outgrown workspaces: never freed, a captured CUDA graph may still point at them
 
 torch::Tensor workspace_for(const torch::Tensor &like, size_t bytes) {
     std::lock_guard<std::mutex> lock(g_ws_mutex);
@@ -154,6 +161,7 @@ torch::Tensor workspace_for(const torch::Tensor &like, size_t bytes) {
         // grow generously so that the allocation happens once (and never during graph capture of a later call)
         const size_t cap = std::max<size_t>(bytes, 8u << 20);
         torch::Tensor ws = torch::zeros({(int64_t)cap}, torch::TensorOptions().dtype(torch::kUInt8).device(like.device()));
+        if (it != g_ws.end()) g_ws_retired.push_back(it->second);
         g_ws[key] = ws;
         return ws;
     }

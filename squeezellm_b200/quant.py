@@ -20,6 +20,8 @@ as the reference, so `llama.py`-style loaders work unchanged.  Differences, all 
 There is NO CPU fallback: importing this module requires the compiled extension, and forward() requires
 CUDA tensors (the extension raises otherwise).
 """
+import glob
+import importlib.util
 import math
 import os
 import sys
@@ -29,15 +31,31 @@ import torch
 import torch.nn as nn
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-if _PKG not in sys.path:  # lets `import quant_cuda` resolve to the in-tree extension, as quant.py:5 expects
-    sys.path.insert(0, _PKG)
-try:
-    import quant_cuda  # noqa: E402
-except ImportError as e:  # fail loudly: no silent eager fallback
-    raise ImportError(
-        "squeezellm_b200: the compiled CUDA extension `quant_cuda` is missing; build it with "
-        "`python -m squeezellm_b200.build` (needs nvcc, sm_100a). No CPU fallback exists."
-    ) from e
+
+
+def _load_extension():
+    """Load the in-tree extension as top-level module `quant_cuda` (the name the reference's quant.py:5 imports) WITHOUT touching
+    sys.path: putting the package directory there would make build / quant / runtime / ... importable as top-level modules and
+    shadow a user's own modules of those names."""
+    if "quant_cuda" in sys.modules and hasattr(sys.modules["quant_cuda"], "lutgemv_fused"):
+        return sys.modules["quant_cuda"]
+    cands = sorted(glob.glob(os.path.join(_PKG, "quant_cuda*.so")))
+    if not cands:
+        raise ImportError(
+            "squeezellm_b200: the compiled CUDA extension `quant_cuda` is missing; build it with "
+            "`python -m squeezellm_b200.build` (needs nvcc, sm_100a). No CPU fallback exists.")
+    spec = importlib.util.spec_from_file_location("quant_cuda", cands[0])
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+    except ImportError as e:  # fail loudly: no silent eager fallback
+        raise ImportError(f"squeezellm_b200: cannot load {cands[0]}: {e}. Rebuild with `python -m squeezellm_b200.build`. "
+                          "No CPU fallback exists.") from e
+    sys.modules["quant_cuda"] = mod
+    return mod
+
+
+quant_cuda = _load_extension()
 
 
 def round_to_nearest_pole_sim(w, poles):
@@ -72,6 +90,7 @@ class QuantLinearLUT(nn.Module):
     """Drop-in layer replacement (reference quant.py:28)."""
 
     use_fused = True  # class-wide switch: fused single-launch forward vs the reference's 12-symbol sequence
+    # codebook precision of the fused path is process-wide: quant_cuda.set_lut_mode("exact" | "fp16")  (include/sqllm_b200.h)
 
     def __init__(self, bits, infeatures, outfeatures, bias, include_sparse=False, numvals=0, topX=0,
                  balanced=False, num_nonzero_per_thread=10):

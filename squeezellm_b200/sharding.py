@@ -119,6 +119,7 @@ class PeerExchange:
     FLAG, STATE, ERROR, DATA = 0, 64, 128, 4096
 
     def __init__(self, rank, world, device, arena_bytes=8 << 20, group=None):
+        """Collective: every rank of `group` must construct its PeerExchange at the same point (ends with a barrier)."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         self.rank, self.world, self.device = rank, world, device
@@ -131,6 +132,7 @@ class PeerExchange:
         self.peer_base = int(self.hdl.buffer_ptrs_dev)
         self.offsets, self.next = {}, self.DATA
         self.arena_bytes = arena_bytes
+        self.calls, self.check_every = 0, 4096   # forward() polls the error word every check_every calls (0 = never; check() is public)
 
     def _slot(self, name, members, n_full, dtype):
         key = (name, members, n_full, dtype)
@@ -149,6 +151,9 @@ class PeerExchange:
         [members, n_full] vector holding every rank's slices once the launch has completed (stream order)."""
         from .quant import quant_cuda
         off, view = self._slot(name, members, n_full, x.dtype)
+        self.calls += 1
+        if self.check_every and self.calls % self.check_every == 0 and not torch.cuda.is_current_stream_capturing():
+            self.check()  # surfaces a timed-out wait in the product path (costs a device synchronisation: every check_every calls only)
         rows, cols, vals, fr, fri = layer._sparse_args()
         quant_cuda.lutgemv_fused_exchange(x.contiguous().reshape(-1), layer.qweight, layer.lookup_table, layer.bits, layer.bias,
                                           rows, cols, vals, fr, fri, self.peer_base, off, self.FLAG, self.STATE, self.ERROR,
@@ -156,8 +161,25 @@ class PeerExchange:
         return view
 
     def error(self):
-        """True if some wait inside a kernel timed out (a peer never delivered)."""
+        """True if some wait inside a kernel timed out (a peer never delivered).  Synchronises the device."""
         return bool(self.arena[self.ERROR:self.ERROR + 4].view(torch.int32).item())
+
+    def check(self):
+        """Raise if the error word is set: after a timeout the vector that call delivered is incomplete and every later wait is
+        skipped (the kernel does not block on a dead peer twice), so results from that point on are not valid."""
+        if self.error():
+            raise RuntimeError("PeerExchange: an in-kernel wait for a peer rank timed out (2 s); results since then are incomplete. "
+                               "Call resync() on every rank once all ranks are alive again.")
+
+    def resync(self):
+        """Collective: bring every rank's counters back to a common, clean state after a timeout (or at any quiescent point).
+        All ranks must call it with no exchange launch in flight."""
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self.arena[:self.DATA].zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
 
 
 class ShardedSiblingGroup:
@@ -237,6 +259,10 @@ class ShardedSiblingGroup:
             self.launches += 1
         self._pending.discard(i)
         y = self._y[..., i, :]
+        if self.peer is not None and self.compute is None:
+            # the peer path returns a view of a persistent arena slot that the next call of this layer overwrites (remotely, from
+            # other ranks): hand out a private copy, like nn.Linear would (N elements - nothing next to the matvec)
+            y = y.clone()
         if y.dim() < x.dim():                      # decode-shaped input [1, 1, K] -> [1, 1, N] like QuantLinearLUT.forward
             y = y.reshape(x.shape[:-1] + (self.n_full,))
         if not self._pending:
@@ -261,4 +287,12 @@ def shard_model(model, rank, world, peer=None, group=None, siblings=(("q_proj", 
         for n, child in mod.named_children():
             if isinstance(child, QuantLinearLUT) and n not in taken and child._sibling_group is None:
                 groups.append(ShardedSiblingGroup([child], rank, world, f"{mod_name}.{n}", peer=peer, group=group))
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            # ranks finish the CPU-side sharding at different times; the in-kernel waits are bounded (2 s), so nobody may start
+            # exchanging before everybody is ready
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            dist.barrier(group=group)
     return groups

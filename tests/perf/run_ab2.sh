@@ -1,0 +1,9 @@
+#!/bin/bash
+# same-box A/B of two harness binaries (previous vs current build)
+run() { bin=$1; bits=$2; sh=$3; sp=$4; shift 4; out=$(env "$@" timeout 120 ./tests/perf/$bin $bits $sh 16 1 $sp 2>&1 | head -1); echo "$bin [sparse=$sp $*] $out"; }
+for sh in "4096 4096" "4096 12288" "4096 22016" "11008 4096" "4096 18944"; do
+  for bin in th_v2_prev th_v2; do
+    run $bin 4 "$sh" 2 SQLLM_X=1
+    run $bin 4 "$sh" 2 SQLLM_LUT_MODE=fp16
+  done
+done

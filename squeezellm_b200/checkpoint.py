@@ -10,13 +10,21 @@ This module is the glue the reference keeps inline in llama.py:136-185 (`load_qu
     state = torch.load(path)                       # reference checkpoint, unchanged
     load_quantized(model, state, wbits=4, include_sparse=True, topX=10)
     model.cuda(); fuse_siblings(model)             # optional: squeezellm_b200.fusion
+`save_checkpoint` / `load_checkpoint` add the file level: the reference's `torch.save` pickle + `quant_config.json` sidecar
+({"wbits": N}, quantization/pack.py:184-190) or - same tensors, same names - a `.safetensors` file whose metadata carries the
+sidecar's content and the `sparse_threshold.*` integers (safetensors stores tensors only).
 Nothing here touches the GPU.
 """
+import json
+import os
+
+import torch
 import torch.nn as nn
 
 from .quant import QuantLinearLUT, make_quant_lut
 
-__all__ = ["find_linear_layers", "split_sparse_thresholds", "merge_sparse_thresholds", "load_quantized", "quantized_state_dict"]
+__all__ = ["find_linear_layers", "split_sparse_thresholds", "merge_sparse_thresholds", "load_quantized", "quantized_state_dict",
+           "write_quant_config", "read_quant_config", "save_checkpoint", "load_checkpoint"]
 
 PREFIX = "sparse_threshold."
 
@@ -75,3 +83,69 @@ def quantized_state_dict(model):
     numvals = {name: int(m.vals.numel()) for name, m in model.named_modules()
                if isinstance(m, QuantLinearLUT) and m.include_sparse and hasattr(m, "vals")}
     return merge_sparse_thresholds(model.state_dict(), numvals)
+
+
+# ---- files ----------------------------------------------------------------------------------------------------------------
+CONFIG_NAME = "quant_config.json"
+
+
+def write_quant_config(directory, wbits, **extra):
+    """The sidecar pack.py:184-190 writes next to the checkpoint: {"wbits": N} (extra keys are allowed, the reference ignores them)."""
+    data = {"wbits": int(wbits)}
+    data.update(extra)
+    path = os.path.join(directory or ".", CONFIG_NAME)
+    with open(path, "w") as f:
+        json.dump(data, f, indent=4)
+    return path
+
+
+def read_quant_config(path_or_dir):
+    """-> dict of the sidecar that sits next to a checkpoint file (or in a directory); {} if there is none."""
+    d = path_or_dir if os.path.isdir(path_or_dir) else os.path.dirname(path_or_dir)
+    path = os.path.join(d or ".", CONFIG_NAME)
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        return json.load(f)
+
+
+def save_checkpoint(model, path, wbits, write_config=True):
+    """Write the model's packed checkpoint.  `*.safetensors`: tensors by safetensors, thresholds + wbits in the metadata;
+    anything else: exactly what quantization/pack.py writes (torch.save of the state dict + sparse_threshold.* ints)."""
+    state = quantized_state_dict(model)
+    if path.endswith(".safetensors"):
+        from safetensors.torch import save_file
+        clean, numvals = split_sparse_thresholds(state)
+        meta = {"format": "pt", "wbits": str(int(wbits)), "sparse_threshold": json.dumps(numvals)}
+        save_file({k: v.detach().cpu().contiguous().clone() for k, v in clean.items()}, path, metadata=meta)  # clone: stacked siblings share storage
+    else:
+        torch.save({k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in state.items()}, path)
+    if write_config:
+        write_quant_config(os.path.dirname(path), wbits)
+    return path
+
+
+def load_checkpoint(model, path, wbits=None, include_sparse=None, topX=0, skip=("lm_head",)):
+    """Read a packed checkpoint file (reference pickle or .safetensors) into `model` (see load_quantized).  `wbits` defaults to the
+    sidecar's / metadata's value, `include_sparse` to "the file has sparse thresholds".  Returns load_quantized's result."""
+    cfg = read_quant_config(path)
+    if path.endswith(".safetensors"):
+        from safetensors import safe_open
+        state, meta = {}, {}
+        with safe_open(path, framework="pt", device="cpu") as f:
+            meta = f.metadata() or {}
+            for k in f.keys():
+                state[k] = f.get_tensor(k)
+        numvals = json.loads(meta.get("sparse_threshold", "{}"))
+        state = merge_sparse_thresholds(state, numvals)
+        if "wbits" in meta:
+            cfg.setdefault("wbits", int(meta["wbits"]))
+    else:
+        state = torch.load(path, map_location="cpu", weights_only=False)
+    if wbits is None:
+        if "wbits" not in cfg:
+            raise ValueError(f"wbits not given and no {CONFIG_NAME} / metadata next to {path}")
+        wbits = int(cfg["wbits"])
+    if include_sparse is None:
+        include_sparse = any(k.startswith(PREFIX) for k in state)
+    return load_quantized(model, state, wbits, include_sparse=include_sparse, topX=topX, skip=skip)

@@ -1275,6 +1275,7 @@ __global__ void unpack_kernel(int bits, const uint32_t *__restrict__ q, int K, i
 }
 
 #include "lutgemv_v2.cuh"
+#include "lutgemm_batched.cuh"
 
 // shared-window address at which a kernel without static shared memory sees its dynamic shared memory (the v2 carve-up aligns
 // tables to their own size - up to 64 KB - so the host needs the real address, not a worst case; the kernel re-checks it)
@@ -1762,6 +1763,53 @@ int launch2(const sqllm_lutgemv_args *a, int variant, bool fused, v2::P2 &p, cud
     return SQLLM_OK;
 }
 
+// ---- batched symbols: tile kernel + outlier kernels (lutgemm_batched.cuh) ----------------------------------------------
+bool g_batched_attr[64] = {};
+int launch_batched(const sqllm_lutgemv_args *a, cudaStream_t st) {
+    using namespace batched;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(SQLLM_ECUDA, "cudaGetDevice failed");
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_state_mu);
+        if (!g_batched_attr[dev]) {
+            if (cudaFuncSetAttribute(lutgemm_batched_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+                cudaFuncSetAttribute(lutgemm_batched_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                return fail(SQLLM_ECUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+            g_batched_attr[dev] = true;
+        }
+    }
+    const int K = a->in_features, N = a->out_features, B = a->batch;
+    const int XU = a->bits == 4 ? 8 : 32, tab = a->bits == 4 ? CB<4>::TAB : CB<3>::TAB;
+    PB p;
+    p.qw = reinterpret_cast<const uint32_t *>(a->qweight); p.lut = a->lookup_table; p.x = a->vec; p.mul = a->mul;
+    p.K = K; p.N = N; p.B = B; p.R = K / XU;
+    // K-slabs: the BT x rows of a slab sit in shared memory next to the table and the partial sums; <= 2048 inputs per slab keeps a
+    // CTA under 90 KB, i.e. two CTAs (16 warps) per SM
+    int slabs = (K + 2047) / 2048;
+    p.ks = 2 * ((p.R + 2 * slabs - 1) / (2 * slabs));
+    slabs = (p.R + p.ks - 1) / p.ks;
+    const int kslab = p.ks * XU;
+    const size_t smem = (size_t)2 * tab + (size_t)BT * (kslab * 4 + 16) + (size_t)BW * BT * STRIP * 4;
+    if (smem > 227 * 1024) return fail(SQLLM_EINVAL, "batched tile needs %zu B of shared memory", smem);
+    const int strips = (N + STRIP - 1) / STRIP, btiles = (B + BT - 1) / BT;
+    if (btiles > 65535) return fail(SQLLM_EINVAL, "batch=%d is too large for one call (max %d)", B, 65535 * BT);
+    const dim3 grid(strips, slabs, btiles);
+    if (a->bits == 4) lutgemm_batched_kernel<4><<<grid, BTHREADS, smem, st>>>(p);
+    else lutgemm_batched_kernel<3><<<grid, BTHREADS, smem, st>>>(p);
+    if (a->rows) {
+        const dim3 blk(32, 8), g((N + 7) / 8, std::min((B + 31) / 32, 64));
+        csr_batched_kernel<<<g, blk, 0, st>>>(a->rows, a->cols, a->vals, a->vec, a->mul, K, N, B);
+    }
+    if (a->full_rows && a->topX > 0) {
+        if (a->topX > 256) return fail(SQLLM_EINVAL, "batched path supports topX <= 256");
+        const int per = 256 / a->topX;
+        dense_rows_batched_kernel<<<(B + per - 1) / per, per * a->topX, 0, st>>>(a->full_rows, a->full_row_indices, a->topX, a->vec, a->mul, K, N, B);
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SQLLM_ECUDA, "batched launch failed: %s", cudaGetErrorString(e));
+    return SQLLM_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -1818,6 +1866,14 @@ int sqllm_lutgemv(const sqllm_lutgemv_args *a, void *stream) {
     if (a->batch < 1) return fail(SQLLM_EINVAL, "batch must be >= 1");
     if (reinterpret_cast<uintptr_t>(a->vec) & 15) return fail(SQLLM_EINVAL, "vec must be 16-byte aligned");
     const bool hyb = a->full_rows && a->topX > 0;
+    if (a->batch >= 2) {
+        static int loop_mode = -1;  // SQLLM_BATCHED=loop: one batch-1 launch per row, as in round 1 (A/B runs)
+        {
+            std::lock_guard<std::recursive_mutex> lk(g_state_mu);
+            if (loop_mode < 0) { const char *e = getenv("SQLLM_BATCHED"); loop_mode = (e && !strcmp(e, "loop")) ? 1 : 0; }
+        }
+        if (!loop_mode) return launch_batched(a, static_cast<cudaStream_t>(stream));
+    }
     if (kernel_sel() == 2 && a->out_features >= STRIP) {
         v2::P2 q;
         memset(&q, 0, sizeof(q));

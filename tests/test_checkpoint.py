@@ -1,5 +1,7 @@
 """Checkpoint glue (squeezellm_b200/checkpoint.py): a reference-format state dict (buffers + sparse_threshold.* ints) loads into
 a model whose Linears are replaced on the fly, and saving gives the same dict back.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -79,3 +81,34 @@ def test_sparse_checkpoint_without_thresholds_is_rejected_and_missing_dense_rows
     assert sorted({k.rsplit(".", 1)[1] for k in res.missing_keys}) == ["full_row_indices", "full_rows"]
     q = net.layers[0].q_proj
     assert q.full_rows.shape == (64, 10) and not q.full_rows.any() and not q.full_row_indices.any()
+
+
+@pytest.mark.parametrize("ext", ["pt", "safetensors"])
+@pytest.mark.parametrize("bits,sparse,topx", [(4, False, 0), (3, True, 5)], ids=["w4-dense", "w3-hybrid"])
+def test_checkpoint_files_roundtrip_with_quant_config_sidecar(tmp_path, ext, bits, sparse, topx):
+    """File level: the reference's torch.save pickle and the .safetensors variant, both with the quant_config.json sidecar
+    (quantization/pack.py:184-190); wbits / include_sparse are recovered from the files when not given."""
+    import json
+    state, expect = _reference_style_state(bits, sparse, topx)
+    net = Net()
+    ck.load_quantized(net, state, bits, include_sparse=sparse, topX=topx)
+    path = str(tmp_path / f"model.{ext}")
+    ck.save_checkpoint(net, path, bits)
+    assert json.load(open(tmp_path / "quant_config.json")) == {"wbits": bits}
+    assert ck.read_quant_config(path) == {"wbits": bits} and ck.read_quant_config(str(tmp_path)) == {"wbits": bits}
+    net2 = Net()
+    res = ck.load_checkpoint(net2, path, topX=topx)  # wbits from the sidecar, include_sparse from the thresholds in the file
+    assert not res.unexpected_keys and not res.missing_keys
+    a, b = ck.quantized_state_dict(net), ck.quantized_state_dict(net2)
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]) if torch.is_tensor(a[k]) else a[k] == b[k], k
+    if ext == "pt":  # the pickle is exactly what pack.py writes: a plain dict with int thresholds
+        raw = torch.load(path, weights_only=False)
+        assert all(isinstance(raw[k], int) for k in raw if k.startswith(ck.PREFIX)) and (len([k for k in raw if k.startswith(ck.PREFIX)]) == (6 if sparse else 0))
+    os.remove(tmp_path / "quant_config.json")
+    if ext == "safetensors":   # metadata carries wbits too
+        ck.load_checkpoint(Net(), path, topX=topx)
+    else:
+        with pytest.raises(ValueError, match="wbits"):
+            ck.load_checkpoint(Net(), path, topX=topx)

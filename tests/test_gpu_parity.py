@@ -135,11 +135,11 @@ def test_matvec_module_vs_reference_kernel(qc, ref, shape):
     assert rel_err(ours.cpu().numpy(), theirs.cpu().numpy()) < REL_TOL
 
 
-@pytest.mark.parametrize("shape", [s for s in SHAPES if s[1] <= 512] + [(4, 4096, 4096, 0.0045, 10, True, False)],
+@pytest.mark.parametrize("shape", [s for s in SHAPES if s[1] <= 512] + [(4, 4096, 4096, 0.0045, 10, True, False), (3, 11008, 4096, 0.0045, 10, True, True)],
                          ids=lambda s: f"w{s[0]}-{s[1]}x{s[2]}-t{s[4]}")
-def test_batched_symbols_vs_oracle_and_reference(qc, ref, shape):
+@pytest.mark.parametrize("batch", [2, 5, 16, 64])
+def test_batched_symbols_vs_oracle_and_reference(qc, ref, shape, batch):
     bits, K, N, sp, topx, nz, skew = shape
-    batch = 5
     L = orc.make_layer(bits, K, N, sparsity=sp, topX=topx, seed=3, skew=skew, nonzero_full_rows=nz)
     if topx and sp == 0:
         L["full_rows"] = L["full_row_indices"] = None

@@ -331,6 +331,9 @@ def main():
     ap.add_argument("--lut", default="both", choices=["both", "exact", "fp16"],
                     help="codebook precision: exact = fp32 as stored (headline), fp16 = pair tables; both = headline exact + a lut_fp16 object")
     ap.add_argument("--blocks", type=int, default=5, help="timed blocks of --steps steps each; the median block is reported")
+    ap.add_argument("--per-shape", action="store_true",
+                    help="also time each of the step's launch types on its own (one CUDA graph of `layers` launches over every layer's "
+                         "distinct weights, CUDA events) and add a per_shape object: us per launch, GB/s and roofline fraction per type")
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload])
     if args.layers:
@@ -484,7 +487,56 @@ def main():
         return {"ms_step": ms / args.steps, "e2e_ms_step": e2e_ms / args.steps, "blocks_ms": [round(b, 4) for b in blocks],
                 "graphed": graphed, "clocks": clocks}
 
+    def per_shape(lut_mode):
+        """us per launch for each launch type of the step: a graph with one launch per decoder layer (every layer's own weights, LUT
+        and outlier arrays, so nothing is L2-resident), replayed 3 + 10 times, device-timed."""
+        quant_cuda.set_lut_mode(lut_mode)
+        peak = peaks()[0]
+        groups = [("qkv" if not args.no_fuse else "q", ("q_proj", "k_proj", "v_proj") if not args.no_fuse else ("q_proj",), "hidden"),
+                  ("o", ("o_proj",), "hidden"), ("gate_up" if not args.no_fuse else "gate", ("gate_proj", "up_proj") if not args.no_fuse else ("gate_proj",), "hidden"),
+                  ("down", ("down_proj",), "ffn")]
+        out = {}
+        for gname, names, kin in groups:
+            xin = torch.randn(cfg[kin], device=dev).half()
+
+            def run():
+                for L in layers:
+                    for n in names:
+                        L[n](xin)
+            st = torch.cuda.Stream()
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                run(); run()
+            torch.cuda.current_stream().wait_stream(st)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                run()
+            for _ in range(3):
+                g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (10 * len(layers))
+            nb = 0
+            for n in names:
+                m = layers[0][n]
+                nnz = int(m.vals.numel()) if hasattr(m, "vals") and m.vals is not None and m.include_sparse else 0
+                nb += alg_bytes(cfg["bits"], m.infeatures, m.outfeatures, nnz, cfg["topX"] if nnz else 0)
+            if not args.no_fuse and len(names) > 1:   # stacked: one x read and one launch for all members
+                nb -= (len(names) - 1) * cfg[kin] * 4
+            out[gname] = {"us_per_launch": us, "algorithmic_bytes": nb, "GBps": nb / us / 1e3, "frac": nb / us / 1e3 / peak,
+                          "K": cfg[kin], "N": sum(layers[0][n].outfeatures for n in names)}
+        quant_cuda.set_lut_mode("exact")
+        return out
+
     head_mode = "fp16" if args.lut == "fp16" else "exact"
+    shapes = None
+    if args.per_shape and world == 1:
+        shapes = {"exact": per_shape("exact"), "fp16": per_shape("fp16")}
     main_run = measure(head_mode, True)
     extra_run = measure("fp16", False) if args.lut == "both" else None
 
@@ -550,6 +602,8 @@ def main():
                      "algorithmic_bytes_per_step_per_gpu": nbytes, "frac_of_nominal_8000": achieved / 8000.0},
         "parity_check": parity,
     }
+    if shapes is not None:
+        out["per_shape"] = shapes
     if extra_run is not None:
         a2 = nbytes / (extra_run["ms_step"] * 1e-3) / 1e9
         out["lut_fp16"] = {"value": 1e3 / extra_run["ms_step"], "unit": "tokens/s", "ms_per_step": extra_run["ms_step"],

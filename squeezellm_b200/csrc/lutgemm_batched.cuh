@@ -64,10 +64,12 @@ __device__ __forceinline__ void fma_rows(float (&acc)[BT][4], const float (&wv)[
         const float4 xa = lds_v4(xaddr + b * xpitch), xb = lds_v4(xaddr + b * xpitch + 16);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            float a = acc[b][t];
-            a = fmaf(wv[t][0], xa.x, a); a = fmaf(wv[t][1], xa.y, a); a = fmaf(wv[t][2], xa.z, a); a = fmaf(wv[t][3], xa.w, a);
-            a = fmaf(wv[t][4], xb.x, a); a = fmaf(wv[t][5], xb.y, a); a = fmaf(wv[t][6], xb.z, a); a = fmaf(wv[t][7], xb.w, a);
-            acc[b][t] = a;
+            // the 8 products of this position first, then ONE add into the running sum: the running sum sees K/8/BW additions instead of
+            // K/BW dependent FMAs, which keeps the batched results as close to the fp64 oracle as the batch-1 kernel's
+            float d = wv[t][0] * xa.x;
+            d = fmaf(wv[t][1], xa.y, d); d = fmaf(wv[t][2], xa.z, d); d = fmaf(wv[t][3], xa.w, d);
+            d = fmaf(wv[t][4], xb.x, d); d = fmaf(wv[t][5], xb.y, d); d = fmaf(wv[t][6], xb.z, d); d = fmaf(wv[t][7], xb.w, d);
+            acc[b][t] += d;
         }
     }
 }
@@ -214,14 +216,14 @@ __global__ void dense_rows_batched_kernel(const float *__restrict__ full_rows, c
     const int c = __ldg(fri + j);
     if (c < 0 || c >= N) return;
     const float *xb = x + (size_t)b * K;
-    float a0 = 0.f, a1 = 0.f;
+    double a0 = 0.0, a1 = 0.0;  // K terms in two chains: fp64 keeps them at the oracle's precision (K * topX * B FMAs - nothing)
     int k = 0;
     for (; k + 1 < K; k += 2) {
-        a0 += __ldg(full_rows + (size_t)k * topX + j) * __ldg(xb + k);
-        a1 += __ldg(full_rows + (size_t)(k + 1) * topX + j) * __ldg(xb + k + 1);
+        a0 += (double)__ldg(full_rows + (size_t)k * topX + j) * (double)__ldg(xb + k);
+        a1 += (double)__ldg(full_rows + (size_t)(k + 1) * topX + j) * (double)__ldg(xb + k + 1);
     }
-    if (k < K) a0 += __ldg(full_rows + (size_t)k * topX + j) * __ldg(xb + k);
-    atomicAdd(mul + (size_t)b * N + c, a0 + a1);
+    if (k < K) a0 += (double)__ldg(full_rows + (size_t)k * topX + j) * (double)__ldg(xb + k);
+    atomicAdd(mul + (size_t)b * N + c, (float)(a0 + a1));
 }
 
 }  // namespace batched

@@ -4,7 +4,7 @@
 // Same job as lutgemv_kernel (v1): y[c] (+)= sum_k LUT[c][idx(k,c)] * x[k]  (+ CSR outliers + topX dense rows), replacing
 // squeezellm/quant_cuda_kernel.cu:741-880 (LUT GEMV), :1040-1059 (SPMV_ATOMIC), :1092-1123 (DenseMatVecKernel).
 // What changed and why (measurements: profiles/r02_*):
-//   * grid = #SMs, 21 warps per CTA: 16 consumer warps, 1 TMA producer warp, 2 table-builder warps, 2 sparse warps.  v1 ran 3 CTAs x 8 consumer warps per SM;
+//   * grid = #SMs, 23 warps per CTA: 16 consumer warps, 1 TMA producer warp, 2 table-builder warps, 4 sparse warps.  v1 ran 3 CTAs x 8 consumer warps per SM;
 //     two thirds of its executed instructions on a 4096x4096 layer were per-CTA prologue/epilogue bookkeeping (ncu, r01).
 //   * weights arrive as 2-D TMA boxes (cp.async.bulk.tensor.2d): stages are aligned to the CTA's strip segments, so a full stage is
 //     ONE box of 64 columns x 32 units (8 KB / 24 KB) issued by one lane of the producer warp; the ragged last stage of a segment
@@ -28,21 +28,26 @@ constexpr int WARP_PROD = NWC;                  // TMA producer
 constexpr int WARP_BLD = NWC + 1;               // first of the 2 table-builder warps
 constexpr int NBW = 2;
 constexpr int WARP_SP = WARP_BLD + NBW;         // first of the sparse warps
-constexpr int NSPW = 2;
-constexpr int THREADS2 = (NWC + 1 + NBW + NSPW) * 32;  // 672
+constexpr int NSPW = 4;                         // sparse warps: their shared-memory accesses queue behind the consumers' (the LSU pipe is
+                                                // saturated), so outlier work is latency-bound per warp - four warps, four times the progress
+constexpr int THREADS2 = (NWC + 1 + NBW + NSPW) * 32;  // 736 (641..768 threads: 80 registers per thread)
 constexpr int NCT = NWC * 32;                   // consumer threads
 constexpr int NBT = NBW * 32;                   // builder threads: one per column slot of a strip
 constexpr int SU2 = 2 * NWC;                    // units per stage (one pair per consumer warp)
 constexpr int MAXD = 16;                        // ring depth limit (mbarrier slots)
-constexpr int CSR_CH2 = 1024;                   // CSR elements staged per chunk and sparse warp
+constexpr int SP_CH = 256;                      // sparse warp: non-zeros per staged chunk (two chunk buffers per warp)
+constexpr int SP_ROWS = 255;                    // owned rows whose pointers / sums are kept in shared memory (CTA-wide)
+constexpr int SP_BYTES = 2 * SP_CH * 8;         // per sparse warp: 2 x (cols + vals) = 4 KB
 constexpr int HYB_R2 = 11;
 static_assert(NBT == STRIP, "one builder thread per column of a strip");
 // shared-memory carve-up, offsets from a 128-byte aligned base
 constexpr int OFF_BAR = 0;                      // full[s] at +8s, empty[s] at +128+8s, tfull[b] at +256+8b, tfree[b] at +272+8b
 constexpr int OFF_SACC = 512;                   // float [2][64]: per-strip sums of the consumer warps (red.shared.add), ping-pong by strip parity
-constexpr int OFF_CSR = OFF_SACC + 2 * STRIP * 4;            // per sparse warp: cols[CSR_CH2] + vals[CSR_CH2]
-constexpr int OFF_LUT = OFF_CSR + NSPW * CSR_CH2 * 8;        // raw fp32 LUT rows of the strip the builders work on (64 columns x 16 values)
-constexpr int OFF_X = OFF_LUT + STRIP * 16 * 4;              // x (fp16 or fp32), then [ring stages][table 0][table 1][ring stages]
+constexpr int OFF_CSR = OFF_SACC + 2 * STRIP * 4;            // per sparse warp: 2 x {int cols[SP_CH], float vals[SP_CH]}
+constexpr int OFF_SROW = OFF_CSR + NSPW * SP_BYTES;          // CTA-wide: int srow[SP_ROWS + 1], float srowacc[SP_ROWS + 1]
+constexpr int OFF_LUT = OFF_SROW + 2 * (SP_ROWS + 1) * 4;        // 2 x raw fp32 LUT rows of a strip (64 columns x 16 values), staged ahead by the builders
+constexpr int LUTBUF = STRIP * 16 * 4;
+constexpr int OFF_X = OFF_LUT + 2 * LUTBUF;                  // x (fp16 or fp32), then [ring stages][table 0][table 1][ring stages]
 static_assert(OFF_X % 128 == 0, "x must stay 128-byte aligned");
 
 struct P2 {
@@ -297,8 +302,8 @@ __device__ __forceinline__ void math2(const Fetch<BITS, XH> &F, const int jsel, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// Sparse warps (2 per CTA).  CSR rows (= output channels) are spread evenly over the CTAs (csr_rpc consecutive rows each) and
-// split between the CTA's two sparse warps; warp 0 also takes the CTA's k-slice of the topX dense rows.  Everything static (row
+// Sparse warp(s) (NSPW per CTA).  CSR rows (= output channels) are spread evenly over the CTAs (csr_rpc consecutive rows each; split
+// between the CTA's sparse warps if there are several); warp 0 also takes the CTA's k-slice of the topX dense rows.  Everything static (row
 // pointers, the first cols/vals group, dense-row values) is requested before the x barrier; x comes from shared memory.
 // Per-row sums are taken in storage order; results go out as one red.add per row.
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -317,9 +322,9 @@ template <bool XH, bool FUSED>
 __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const uint32_t base, const int spw, const int lane, float *acc_out) {
     const int N = p.N;
     const uint32_t xs_u32 = base + OFF_X;
-    int *scols = reinterpret_cast<int *>(sm + OFF_CSR + spw * (CSR_CH2 * 8));
-    float *svals = reinterpret_cast<float *>(sm + OFF_CSR + spw * (CSR_CH2 * 8) + CSR_CH2 * 4);
-    const uint32_t scols_u32 = base + OFF_CSR + spw * (CSR_CH2 * 8), svals_u32 = scols_u32 + CSR_CH2 * 4;
+    const uint32_t stage_u32 = base + OFF_CSR + spw * SP_BYTES;       // this warp's chunk buffer b: cols at +b*SP_CH*8, vals SP_CH*4 further
+    int *srow = reinterpret_cast<int *>(sm + OFF_SROW);               // [SP_ROWS + 1] row pointers of the CTA's rows (FUSED, when they fit)
+    float *srowacc = reinterpret_cast<float *>(srow + SP_ROWS + 1);   // [SP_ROWS + 1] their outlier sums, picked up by the builders
 
     // ---------------- phase A: static data ----------------
     float hfr[HYB_R2];
@@ -337,41 +342,81 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
             hfr[i] = (rs < nsl && k < ke) ? __ldg(p.full_rows + (size_t)k * p.topX + hj) : 0.f;
         }
     }
-    // this warp's CSR rows [r, rb): the CTA's range split 2:3 when warp 0 also has dense rows, evenly otherwise
-    int r = 0, rb = 0;
+    // FUSED: the CSR rows of the strips this CTA OWNS (those that start in its range - it also finishes them), so that outlier sums
+    // never leave the CTA: they go into a shared-memory row accumulator that the builders add when they write y.  (Earlier v2 builds
+    // spread the rows evenly over all CTAs and announced them on the strips' flags: a MEMBAR.GPU per announcement, and every strip owner
+    // waited for some other CTA's sparse warp - the critical path of the kernel on layers with outliers.)
+    // Accumulate mode (the 12 symbols, no owner): rows spread evenly over the CTAs, one red.add per row into `mul`.
+    // The CTA's rows [ca, cb) are split over its NSPW sparse warps (warp 0, which also has the dense rows, takes half a share).
+    int ca = 0, cb = 0;
     if (p.rows) {
-        const int ca = min(N, (int)blockIdx.x * p.csr_rpc), cb = min(N, ca + p.csr_rpc);
-        const int cut = ca + ((cb - ca) * (p.full_rows ? 2 : 1)) / (p.full_rows ? 5 : 2);
-        r = spw == 0 ? ca : cut;
-        rb = spw == 0 ? cut : cb;
-    }
-    int rp = 0, m = 0, gbase = 0, cnt = 0;
-    auto group_begin = [&]() {  // row pointers one per lane, group size by ballot, then stage cols/vals
-        rp = __ldg(p.rows + min(r + lane, rb));
-        gbase = __shfl_sync(0xffffffffu, rp, 0);
-        const bool ok = lane <= min(31, rb - r) && rp - gbase <= CSR_CH2 - 4;
-        m = __popc(__ballot_sync(0xffffffffu, ok)) - 1;  // rp is non-decreasing: the ok lanes are a prefix that includes lane 0
-        const int last = m > 0 ? __shfl_sync(0xffffffffu, rp, m) : gbase;
-        if (p.csr_al16 && m > 0) {
-            gbase &= ~3;  // 16-byte copies from the aligned-down start; the last quad is clipped with the src-size operand
-            cnt = last - gbase;
-            for (int e = 4 * lane; e < cnt; e += 128) {
-                const int nb = min(16, 4 * (cnt - e));
-                cp_async16_clip(scols_u32 + 4 * e, p.cols + gbase + e, nb);
-                cp_async16_clip(svals_u32 + 4 * e, p.vals + gbase + e, nb);
-            }
+        if constexpr (FUSED) {
+            const long long cb0 = (long long)blockIdx.x * p.chunk, cb1 = min((long long)p.T, cb0 + p.chunk);
+            ca = min(N, (int)((cb0 + p.R - 1) / p.R) * STRIP);
+            cb = min(N, (int)((cb1 + p.R - 1) / p.R) * STRIP);
         } else {
-            cnt = m > 0 ? last - gbase : 0;
-            for (int e = lane; e < cnt; e += 32) {
-                cp_async4(scols_u32 + 4 * e, p.cols + gbase + e);
-                cp_async4(svals_u32 + 4 * e, p.vals + gbase + e);
+            ca = min(N, (int)blockIdx.x * p.csr_rpc);
+            cb = min(N, ca + p.csr_rpc);
+        }
+    }
+    int r, rb;
+    {
+        const int tot = cb - ca, w0 = p.full_rows ? tot / (2 * NSPW) : tot / NSPW, rest = tot - w0;
+        r = spw == 0 ? ca : ca + w0 + (int)((long long)rest * (spw - 1) / (NSPW - 1));
+        rb = spw == 0 ? ca + w0 : ca + w0 + (int)((long long)rest * spw / (NSPW - 1));
+    }
+    const int nr = rb - r;
+    const bool local_sums = FUSED && cb - ca <= SP_ROWS;  // the CTA's row pointers and row sums live in shared memory (same rule in the builders)
+    auto emit = [&](int row, float v) {
+        if (local_sums) atomicAdd(srowacc + (row - ca), v);  // shared-memory red: a row can arrive in pieces from different lanes
+        else atomicAdd(acc_out + row, v);
+    };
+    int e_lo = 0, e_hi = 0;
+    if (nr > 0) {
+        if (local_sums)
+            for (int i = lane; i <= nr; i += 32) {
+                srow[r - ca + i] = __ldg(p.rows + r + i);   // (the boundary entry is written by both neighbours, with the same value)
+                if (i < nr) srowacc[r - ca + i] = 0.f;
+            }
+        e_lo = __ldg(p.rows + r);
+        e_hi = __ldg(p.rows + rb);
+    }
+    // This warp's non-zeros [e_lo, e_hi) go to L2 right away (a CTA has ~5-25 KB of outliers and only two small chunks per warp fit the
+    // staging buffers: under a saturated HBM every further chunk would otherwise cost a DRAM round trip of 2-3 us), and are then walked
+    // in chunks of SP_CH staged with 16-byte cp.async into two buffers.  Shared-memory accesses of these warps queue behind the
+    // consumers' (the LSU pipe is what bounds the kernel), i.e. each dependent access costs hundreds of cycles: that is why there are
+    // NSPW warps with independent chains (one warp: 14 us for 3200 non-zeros) and why every step below batches independent loads.
+    for (int e = (e_lo & ~31) + 32 * lane; e < e_hi; e += 32 * 32) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cols + e));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.vals + e));
+    }
+    const bool al16 = p.csr_al16 != 0;
+    const int c_lo = al16 ? (e_lo & ~3) : e_lo;  // chunk grid: 16-byte aligned element index when the arrays are
+    auto stage_chunk = [&](int ci) {              // chunk ci covers elements [c_lo + ci*SP_CH, +SP_CH) -> buffer ci & 1
+        const int t0 = c_lo + ci * SP_CH;
+        const uint32_t dc = stage_u32 + (ci & 1) * (SP_CH * 8), dv = dc + SP_CH * 4;
+        if (t0 < e_hi) {
+            if (al16) {
+                for (int e = 4 * lane; e < SP_CH; e += 128) {
+                    const int nb = min(16, 4 * (e_hi - (t0 + e)));  // the last quad is clipped with the src-size operand: nothing past e_hi is read
+                    if (nb > 0) {
+                        cp_async16_clip(dc + 4 * e, p.cols + t0 + e, nb);
+                        cp_async16_clip(dv + 4 * e, p.vals + t0 + e, nb);
+                    }
+                }
+            } else {
+                for (int e = lane; e < SP_CH && t0 + e < e_hi; e += 32) {
+                    cp_async4(dc + 4 * e, p.cols + t0 + e);
+                    cp_async4(dv + 4 * e, p.vals + t0 + e);
+                }
             }
         }
-        cp_async_commit();
+        cp_async_commit();  // exactly one group per chunk, empty or not
     };
-    if (r < rb) group_begin();
+    stage_chunk(0);
+    stage_chunk(1);
 
-    named_bar_sync(2, NCT + (NBW + NSPW) * 32);  // x is in shared memory (and the previous kernel has completed: the consumers waited on it)
+    named_bar_sync(2, NCT + NSPW * 32);  // x is in shared memory (and the previous kernel has completed: the consumers waited on it)
 
     // ---------------- phase B ----------------
     if (hyb_on) {
@@ -404,59 +449,13 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
                 if (c >= 0 && c < N) atomicAdd(acc_out + c, a);
             }
         }
-    }
-    while (r < rb) {
-        if (m == 0) {  // a single row longer than the staging buffer: straight from global memory, whole warp
-            const int e1 = __shfl_sync(0xffffffffu, rp, 1);
-            float a = 0.f;
-            for (int e = gbase + lane; e < e1; e += 32) a += __ldg(p.vals + e) * xs_load<XH>(xs_u32, __ldg(p.cols + e));
-            a = warp_sum(a);
-            if (lane == 0) atomicAdd(acc_out + r, a);
-            r += 1;
-        } else {
-            cp_async_wait_all();
+        if constexpr (FUSED) {
+            // announce this CTA's dense-row contributions now, early in the kernel: one fence, then a relaxed increment per distinct
+            // strip that holds a dense-row channel (every one of the hc contributing CTAs does this; the owners expect hc arrivals)
+            __threadfence();
             __syncwarp();
-            for (int e = lane; e < cnt; e += 32) svals[e] *= xs_load<XH>(xs_u32, scols[e]);  // products in place
-            __syncwarp();
-            // lane i < m owns row r+i: [a0, a1) in the staged arrays
-            const int a0 = rp - gbase, a1 = __shfl_down_sync(0xffffffffu, rp, 1) - gbase;
-            const int n = lane < m ? a1 - a0 : 0;
-            if (lane < m && n <= 64) {  // short row: sequential sum in storage order (two interleaved chains)
-                float ea = 0.f, eb = 0.f;
-                int e = a0;
-                for (; e + 1 < a1; e += 2) { ea += svals[e]; eb += svals[e + 1]; }
-                if (e < a1) ea += svals[e];
-                if (n > 0) atomicAdd(acc_out + r + lane, ea + eb);
-            }
-            unsigned longm = __ballot_sync(0xffffffffu, n > 64);  // long rows: the whole warp on each, fixed xor tree
-            while (longm) {
-                const int i = __ffs(longm) - 1;
-                longm &= longm - 1;
-                const int b0 = __shfl_sync(0xffffffffu, a0, i), b1 = __shfl_sync(0xffffffffu, a1, i);
-                float a = 0.f;
-                for (int e = b0 + lane; e < b1; e += 32) a += svals[e];
-                a = warp_sum(a);
-                if (lane == 0) atomicAdd(acc_out + r + i, a);
-            }
-            __syncwarp();
-            r += m;
-        }
-        if (r < rb) group_begin();
-    }
-    if constexpr (FUSED) {
-        // Announce this CTA's outlier contributions: one release-increment per strip its CSR rows touch (whatever their nnz) and per
-        // distinct strip that holds a dense-row channel.  The barrier makes both warps' red.adds precede every increment.
-        named_bar_sync(4, NSPW * 32);
-        const int st = spw * 32 + lane;
-        int *flags = p.ws_cnt + 64;
-        if (p.rows) {
-            const int ca = min(N, (int)blockIdx.x * p.csr_rpc), cb = min(N, ca + p.csr_rpc);
-            if (ca < cb)
-                for (int s = ca / STRIP + st; s <= (cb - 1) / STRIP; s += NSPW * 32)
-                    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + s) : "memory");
-        }
-        if (p.full_rows && (int)blockIdx.x < p.hc) {
-            for (int j = st; j < p.topX; j += NSPW * 32) {
+            int *flags = p.ws_cnt + 64;
+            for (int j = lane; j < p.topX; j += 32) {
                 const int c = __ldg(p.fri + j);
                 if (c < 0 || c >= N) continue;
                 bool seen = false;
@@ -464,9 +463,82 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
                     const int c2 = __ldg(p.fri + j2);
                     seen |= (c2 >= 0 && c2 < N && c2 / STRIP == c / STRIP);
                 }
-                if (!seen) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + c / STRIP) : "memory");
+                if (!seen) asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(flags + c / STRIP) : "memory");
             }
         }
+    }
+    int rcur = r;  // first row that still has non-zeros at or after the current chunk
+    const int avg = nr > 0 ? (e_hi - e_lo) / nr : 0;
+    const int LPR = avg > 32 ? 8 : avg > 12 ? 4 : avg > 5 ? 2 : 1;  // lanes per row (power of two)
+    for (int ci = 0; c_lo + ci * SP_CH < e_hi; ++ci) {
+        const int t0 = c_lo + ci * SP_CH, t1 = min(t0 + SP_CH, e_hi), f0 = max(t0, e_lo);
+        const int *scols = reinterpret_cast<const int *>(sm + OFF_CSR + spw * SP_BYTES + (ci & 1) * (SP_CH * 8));
+        float *svals = reinterpret_cast<float *>(sm + OFF_CSR + spw * SP_BYTES + (ci & 1) * (SP_CH * 8) + SP_CH * 4);
+        cp_async_wait_pending<1>();  // all but the newest group have landed: this chunk is there
+        __syncwarp();
+        // products in place: all (col, val) loads of a trip first, then the x gathers, then the stores
+        for (int e0 = f0 - t0 + lane; e0 < t1 - t0; e0 += 256) {
+            int cc[8];
+            float xv[8], vv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool ok = e0 + 32 * j < t1 - t0;
+                cc[j] = ok ? scols[e0 + 32 * j] : 0;
+                vv[j] = ok ? svals[e0 + 32 * j] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = xs_load<XH>(xs_u32, cc[j]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (e0 + 32 * j < t1 - t0) svals[e0 + 32 * j] = vv[j] * xv[j];
+        }
+        __syncwarp();
+        // rows that intersect [f0, t1), 32 / LPR at a time from rcur: LPR lanes share a row (lane part p takes elements p, p + LPR, ...
+        // of the row's piece, four independent loads per trip), their partial sums are folded with shuffles and the row's piece is
+        // added to its sum (a row that straddles chunks arrives in pieces).  LPR grows with the average row length: a dependent
+        // shared-memory trip costs this warp hundreds of cycles, a 50-element row summed by one lane would be 13 of them.
+        while (true) {
+            const int row = rcur + lane / LPR, part = lane & (LPR - 1);
+            int a0 = e_hi, a1 = e_hi;
+            if (row < rb) {
+                a0 = local_sums ? srow[row - ca] : __ldg(p.rows + row);
+                a1 = local_sums ? srow[row - ca + 1] : __ldg(p.rows + row + 1);
+            }
+            const bool inter = row < rb && a0 < t1;
+            const int s0 = max(a0, f0) - t0, s1 = min(a1, t1) - t0;
+            const int n = inter ? s1 - s0 : 0;
+            float ea = 0.f, eb = 0.f, ec = 0.f, ed = 0.f;
+            if (n > 0 && n <= 64 * LPR) {
+                int e = s0 + part;
+                for (; e + 3 * LPR < s1; e += 4 * LPR) {
+                    const float q0 = svals[e], q1 = svals[e + LPR], q2 = svals[e + 2 * LPR], q3 = svals[e + 3 * LPR];
+                    ea += q0; eb += q1; ec += q2; ed += q3;
+                }
+                for (; e < s1; e += LPR) ea += svals[e];
+            }
+            float tot = (ea + eb) + (ec + ed);
+            for (int d = 1; d < LPR; d <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+            if (part == 0 && n > 0 && n <= 64 * LPR) emit(row, tot);
+            unsigned longm = __ballot_sync(0xffffffffu, part == 0 && n > 64 * LPR);  // very long pieces: the whole warp on each
+            while (longm) {
+                const int i = __ffs(longm) - 1;
+                longm &= longm - 1;
+                const int b0 = __shfl_sync(0xffffffffu, s0, i), b1 = __shfl_sync(0xffffffffu, s1, i);
+                float a = 0.f;
+                for (int e = b0 + lane; e < b1; e += 32) a += svals[e];
+                a = warp_sum(a);
+                if (lane == 0) emit(rcur + i / LPR, a);
+            }
+            const int ndone = __popc(__ballot_sync(0xffffffffu, part == 0 && row < rb && a1 <= t1));  // rows are sorted: a prefix
+            rcur += ndone;
+            if (ndone < 32 / LPR || rcur >= rb) break;  // the last row of the pass still has non-zeros beyond this chunk (or no rows are left)
+        }
+        __syncwarp();
+        stage_chunk(ci + 2);  // this buffer is free again
+    }
+    if constexpr (FUSED) {
+        if (!local_sums && cb > ca) __threadfence();  // (more owned rows than the row accumulator holds: sums went to global memory)
+        named_bar_sync(4, (NSPW + NBW) * 32);         // hand-over to the builders: row sums complete
     }
 }
 
@@ -512,6 +584,24 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_launch_dependents();
+    if (warp == WARP_PROD) {
+        // Cold-start latencies (a decode step finds none of a layer's arrays in L2): ask for the two tensor-map descriptors now, and let
+        // every CTA pull a 1/grid slice of the layer's look-up table and row pointers into L2 - the CTAs of a launch start up to ~4 us
+        // apart (they inherit their SM from the previous kernel's CTAs), so the late ones find what the early ones asked for.
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_big)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_small)) : "memory");
+        }
+        const int G = (int)gridDim.x;
+        const size_t lut_lines = ((size_t)N * C::L * 4 + 127) / 128, per = (lut_lines + G - 1) / G;
+        for (size_t i = (size_t)blockIdx.x * per + lane; i < min(lut_lines, ((size_t)blockIdx.x + 1) * per); i += 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.lut) + 128 * i));
+        if (p.rows) {
+            const size_t row_lines = ((size_t)(N + 1) * 4 + 127) / 128, rper = (row_lines + G - 1) / G;
+            for (size_t i = (size_t)blockIdx.x * rper + lane; i < min(row_lines, ((size_t)blockIdx.x + 1) * rper); i += 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.rows) + 128 * i));
+        }
+    }
     __syncthreads();
     float *const acc_out = FUSED ? p.ws_acc : reinterpret_cast<float *>(p.out);
 
@@ -561,6 +651,8 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
         sts_u32(sacc + 4 * bt, 0u);
         sts_u32(sacc + 4 * (STRIP + bt), 0u);
         int *const flags = p.ws_cnt + 64;
+        bool dep_ok = false;
+        auto dep_wait = [&]() { if (!dep_ok) { pdl_wait(); dep_ok = true; } };  // builders never read x: they only need this before writing
         auto flush = [&](int s) {  // strip sums of segment s -> one red.add per column, accumulator back to zero
             const uint32_t a = sacc + 4 * ((s & 1) * STRIP + bt);
             const float v = lds_f32(a);
@@ -576,22 +668,25 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
                 }
             }
         };
+        // The raw LUT rows of the first two strips are requested at once (one cold round trip, not two); later strips two ahead.
         if (nseg > 0) lut_prefetch<BITS>(p, lutbuf, s0, bt);
+        if (nseg > 1) lut_prefetch<BITS>(p, lutbuf + LUTBUF, s0 + 1, bt);
         for (int s = 0; s < nseg; ++s) {
             const int b = s & 1;
-            if (s == 2) named_bar_sync(2, NCT + (NBW + NSPW) * 32);  // from here on we write global memory: the previous kernel must be done
             if (s >= 2) {
+                dep_wait();  // from here on we write global memory: the previous kernel must be done
                 mbar_wait(bar_u32 + 272 + 8 * b, (uint32_t)(((s >> 1) - 1) & 1));
                 flush(s - 2);
             }
-            cp_async_wait_all();
+            if (s + 1 < nseg) cp_async_wait_pending<1>();  // all but the newest group (the next strip's rows) have landed
+            else cp_async_wait_all();
             named_bar_sync(3, NBT);  // the strip's LUT rows are in shared memory, all of them
-            build_table<BITS, MODE>(tab0 + b * C::TAB, lutbuf, bt);
+            build_table<BITS, MODE>(tab0 + b * C::TAB, lutbuf + b * LUTBUF, bt);
             named_bar_sync(3, NBT);  // both warps are done reading the rows (and writing the table)
             if (lane == 0) mbar_arrive(bar_u32 + 256 + 8 * b);
-            if (s + 1 < nseg) lut_prefetch<BITS>(p, lutbuf, s0 + s + 1, bt);  // next strip's rows: long there when they are needed
+            if (s + 2 < nseg) lut_prefetch<BITS>(p, lutbuf + b * LUTBUF, s0 + s + 2, bt);  // this buffer's next strip: long there when it is needed
         }
-        if (nseg <= 2) named_bar_sync(2, NCT + (NBW + NSPW) * 32);
+        dep_wait();
         if constexpr (!FUSED) {
             for (int s = max(0, nseg - 2); s < nseg; ++s) {  // the last two segments
                 mbar_wait(bar_u32 + 272 + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
@@ -600,8 +695,8 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
         } else {
             // ---- finish the strips this CTA owns (those that start in its range).  Every table is built, so the builders have time: while
             //      the consumers are still in the last segment they wait for the other contributors' announcements - dense CTAs holding a
-            //      later part, every CTA whose CSR rows touch the strip, the hc dense-row CTAs if a dense-row channel lies in it - and
-            //      fetch the accumulator.  What is left for the very end is y = accumulator + own last strip (+ bias): no round trip to
+            //      later part, the hc dense-row CTAs if a dense-row channel lies in it (the strips' CSR outliers are summed by this CTA's
+            //      own sparse warp, in shared memory) - and fetch the accumulator.  What is left for the very end is y = accumulator + own last strip (+ bias): no round trip to
             //      L2 after the last weight, no grid-wide step; a CTA leaves as soon as its own strips are complete.
             //      Waits are bounded (2 s, then the workspace error word is set).
             if (nseg >= 2) {
@@ -614,10 +709,6 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             for (int i = bt; i < nown; i += NBT) {
                 const int strip = so0 + i;
                 int expect = (int)((((long long)strip + 1) * R - 1) / p.chunk) - (int)blockIdx.x;  // dense CTAs after this one
-                if (p.rows) {
-                    const int c0 = strip * STRIP, c1 = min(N, c0 + STRIP) - 1;
-                    expect += c1 / p.csr_rpc - c0 / p.csr_rpc + 1;
-                }
                 if (p.full_rows) {
                     bool h = false;
                     for (int j = 0; j < p.topX; ++j) {
@@ -640,9 +731,12 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
                     flags[strip] = 0;
                 }
             }
-            named_bar_sync(3, NBT);  // the others' contributions to every owned strip are complete (acquire above + barrier)
+            named_bar_sync(3, NBT);  // the polls above are through: the others' contributions to every owned strip are complete
+            const float *srowacc = reinterpret_cast<const float *>(sm + OFF_SROW + (SP_ROWS + 1) * 4);
+            const bool local_sums = p.rows && min(N, so1 * STRIP) - min(N, so0 * STRIP) <= SP_ROWS;  // same rule as the sparse warps'
             const int w = p.xw_world ? N / p.xw_members : 0;
             auto store_y = [&](int col, float yv) {
+                if (local_sums) yv += srowacc[col - so0 * STRIP];
                 if (p.bias) yv += __ldg(p.bias + col);
                 if (p.xw_world == 0) {
                     if (p.y_is_half) reinterpret_cast<__half *>(p.out)[col] = __float2half_rn(yv);
@@ -659,30 +753,37 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
                     }
                 }
             };
-            // strips whose own part is already in the accumulator: all owned ones but (if owned) the last segment's
+            // accumulator values first (strips whose own part is already in it: all owned ones but, if owned, the last segment's; and what
+            // the others added to that last one - our own part of it never goes through memory), then wait for this CTA's sparse warps
+            // (their row sums are needed from here on), then the stores
             const int nearly = last_owned ? nown - 1 : nown;
-            for (int i0 = 0; i0 < nearly; i0 += 4) {
-                float vv[4];
+            float vv[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int col = (so0 + i0 + u) * STRIP + bt;
-                    vv[u] = (i0 + u < nearly && col < N) ? __ldcg(p.ws_acc + col) : 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int col = (so0 + i0 + u) * STRIP + bt;
-                    if (i0 + u < nearly && col < N) {
-                        p.ws_acc[col] = 0.f;
-                        store_y(col, vv[u]);
-                    }
-                }
+            for (int u = 0; u < 8; ++u) {
+                const int col = (so0 + u) * STRIP + bt;
+                vv[u] = (u < nearly && col < N) ? __ldcg(p.ws_acc + col) : 0.f;
             }
             float pre = 0.f;
             const int lcol = (s0 + nseg - 1) * STRIP + bt;
-            if (last_owned && nseg > 0 && lcol < N) {
-                pre = __ldcg(p.ws_acc + lcol);   // what the others added to the last strip; our own part never goes through memory
-                p.ws_acc[lcol] = 0.f;
+            if (last_owned && nseg > 0 && lcol < N) pre = __ldcg(p.ws_acc + lcol);
+            named_bar_sync(4, (NSPW + NBW) * 32);  // this CTA's own outlier row sums (sparse warps) are complete
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int col = (so0 + u) * STRIP + bt;
+                if (u < nearly && col < N) {
+                    p.ws_acc[col] = 0.f;
+                    store_y(col, vv[u]);
+                }
             }
+            for (int i = 8; i < nearly; ++i) {  // (more than 8 owned strips: out_features > 75,000 - one at a time)
+                const int col = (so0 + i) * STRIP + bt;
+                if (col < N) {
+                    const float a = __ldcg(p.ws_acc + col);
+                    p.ws_acc[col] = 0.f;
+                    store_y(col, a);
+                }
+            }
+            if (last_owned && nseg > 0 && lcol < N) p.ws_acc[lcol] = 0.f;
             TRACE(8, bt == 0);
             if (nseg > 0) {
                 const int s = nseg - 1;
@@ -738,7 +839,7 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             cp_async_commit();
             cp_async_wait_all();
         }
-        named_bar_sync(2, NCT + (NBW + NSPW) * 32);  // x visible to consumers and sparse warps; builders may write global memory
+        named_bar_sync(2, NCT + NSPW * 32);  // x visible to consumers and the sparse warp
         TRACE(4, tid == 0);
 
         Acc A;

@@ -21,24 +21,33 @@ int main(int argc, char **argv) {
     const int sparse = argc > 6 ? atoi(argv[6]) : 0;  // 1: CSR (0.45 %) + 10 zero dense rows, accumulate; 2: same, fused fp16
 
     const size_t qwords = (size_t)K / 32 * bits * N;
-    const int copies = (size_t)K * N > (64u << 20) ? 3 : 40;
+    // enough distinct copies that the chain never finds a matrix in the 126 MB L2 (>= 400 MB in rotation)
+    const int copies = (int)std::min<size_t>(40, std::max<size_t>(3, (400u << 20) / (qwords * 4) + 1));
     uint32_t *q; float *lut, *x, *y; unsigned long long *trace;
     CK(cudaMalloc(&q, qwords * 4 * copies)); CK(cudaMemset(q, 0x5a, qwords * 4 * copies));
-    CK(cudaMalloc(&lut, (size_t)N * 16 * 4)); CK(cudaMemset(lut, 0, (size_t)N * 16 * 4));
+    // every launch of the chain gets its own weights AND its own look-up table / outlier arrays: a decode step never finds a layer's small
+    // arrays in L2 either (one shared table made the chain ~3 us per launch faster than the real step: r02 notes in profiles/)
+    const size_t lutn = (size_t)N * 16;
+    CK(cudaMalloc(&lut, lutn * 4 * copies)); CK(cudaMemset(lut, 0, lutn * 4 * copies));
     CK(cudaMalloc(&x, K * 4)); CK(cudaMemset(x, 0, K * 4));
     CK(cudaMalloc(&y, (size_t)N * 4 * chain)); CK(cudaMemset(y, 0, (size_t)N * 4 * chain));
     const size_t stride = 1024 * 32;
     CK(cudaMalloc(&trace, stride * 8 * chain)); CK(cudaMemset(trace, 0, stride * 8 * chain));
+    size_t rstride = 0, nstride = 0, fstride = 0;
     int *rows = nullptr, *cols = nullptr, *fri = nullptr; float *vals = nullptr, *fr = nullptr; void *ws = nullptr; size_t wsb = 0; void *xh = nullptr, *yh = nullptr;
     if (sparse) {
         const int per = (int)(0.0045 * K + 0.5); const size_t nnz = (size_t)per * N;
         std::vector<int> hr(N + 1), hc(nnz);
         for (int c = 0; c <= N; ++c) hr[c] = c * per;
         for (size_t i = 0; i < nnz; ++i) hc[i] = (int)((i * 2654435761u) % K);
-        CK(cudaMalloc(&rows, (N + 1) * 4)); CK(cudaMemcpy(rows, hr.data(), (N + 1) * 4, cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&cols, nnz * 4)); CK(cudaMemcpy(cols, hc.data(), nnz * 4, cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&vals, nnz * 4)); CK(cudaMemset(vals, 0, nnz * 4));
-        CK(cudaMalloc(&fr, (size_t)K * 10 * 4)); CK(cudaMemset(fr, 0, (size_t)K * 10 * 4));
+        rstride = ((size_t)N + 1 + 63) / 64 * 64; nstride = (nnz + 63) / 64 * 64; fstride = (size_t)K * 10;
+        CK(cudaMalloc(&rows, rstride * 4 * copies)); CK(cudaMalloc(&cols, nstride * 4 * copies)); CK(cudaMalloc(&vals, nstride * 4 * copies));
+        CK(cudaMemset(vals, 0, nstride * 4 * copies));
+        for (int c = 0; c < copies; ++c) {
+            CK(cudaMemcpy(rows + c * rstride, hr.data(), (N + 1) * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(cols + c * nstride, hc.data(), nnz * 4, cudaMemcpyHostToDevice));
+        }
+        CK(cudaMalloc(&fr, fstride * 4 * copies)); CK(cudaMemset(fr, 0, fstride * 4 * copies));
         CK(cudaMalloc(&fri, 40)); CK(cudaMemset(fri, 0, 40));
         wsb = 16u << 20; CK(cudaMalloc(&ws, wsb)); CK(cudaMemset(ws, 0, wsb));
         CK(cudaMalloc(&xh, K * 2)); CK(cudaMemset(xh, 0, K * 2)); CK(cudaMalloc(&yh, (size_t)N * 2 * chain));
@@ -49,8 +58,9 @@ int main(int argc, char **argv) {
         for (int i = 0; i < chain; ++i) {
             sqllm_lutgemv_args a; memset(&a, 0, sizeof(a));
             a.bits = bits; a.in_features = K; a.out_features = N; a.batch = 1;
-            a.qweight = (const int32_t *)(q + (size_t)(i % copies) * qwords); a.lookup_table = lut; a.vec = x; a.mul = y + (size_t)i * N;
-            if (sparse) { a.rows = rows; a.cols = cols; a.vals = vals; a.full_rows = fr; a.full_row_indices = fri; a.topX = 10; }
+            const int c = i % copies;
+            a.qweight = (const int32_t *)(q + (size_t)c * qwords); a.lookup_table = lut + (size_t)c * lutn; a.vec = x; a.mul = y + (size_t)i * N;
+            if (sparse) { a.rows = rows + c * rstride; a.cols = cols + c * nstride; a.vals = vals + c * nstride; a.full_rows = fr + c * fstride; a.full_row_indices = fri; a.topX = 10; }
             int rc = sparse == 2 ? sqllm_lutgemv_fused(&a, xh, 1, (char *)yh + (size_t)i * N * 2, 1, nullptr, ws, wsb, st) : sqllm_lutgemv(&a, st);
             if (rc) { printf("error: %s\n", sqllm_last_error()); exit(1); }
         }

@@ -21,6 +21,10 @@
 //   * x is staged whole (as fp16 when it is given as fp16), the sparse warps gather it from shared memory.
 #pragma once
 
+#ifndef SQLLM_V2_PIPE
+#define SQLLM_V2_PIPE 0   // 1: two-stage ping-pong word fetch in the consumer loop (measured, not faster: see the loop)
+#endif
+
 namespace v2 {
 
 constexpr int NWC = 16;                         // consumer warps
@@ -368,7 +372,7 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
     const int nr = rb - r;
     const bool local_sums = FUSED && cb - ca <= SP_ROWS;  // the CTA's row pointers and row sums live in shared memory (same rule in the builders)
     auto emit = [&](int row, float v) {
-        if (local_sums) atomicAdd(srowacc + (row - ca), v);  // shared-memory red: a row can arrive in pieces from different lanes
+        if (local_sums) srowacc[row - ca] += v;  // plain read-modify-write: a row belongs to this warp alone and its pieces arrive one after the other
         else atomicAdd(acc_out + row, v);
     };
     int e_lo = 0, e_hi = 0;
@@ -509,12 +513,13 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
             const int n = inter ? s1 - s0 : 0;
             float ea = 0.f, eb = 0.f, ec = 0.f, ed = 0.f;
             if (n > 0 && n <= 64 * LPR) {
-                int e = s0 + part;
-                for (; e + 3 * LPR < s1; e += 4 * LPR) {
-                    const float q0 = svals[e], q1 = svals[e + LPR], q2 = svals[e + 2 * LPR], q3 = svals[e + 3 * LPR];
+                for (int e = s0 + part; e < s1; e += 4 * LPR) {  // four independent (predicated) loads per trip
+                    const float q0 = svals[e];
+                    const float q1 = e + LPR < s1 ? svals[e + LPR] : 0.f;
+                    const float q2 = e + 2 * LPR < s1 ? svals[e + 2 * LPR] : 0.f;
+                    const float q3 = e + 3 * LPR < s1 ? svals[e + 3 * LPR] : 0.f;
                     ea += q0; eb += q1; ec += q2; ed += q3;
                 }
-                for (; e < s1; e += LPR) ea += svals[e];
             }
             float tot = (ea + eb) + (ec + ed);
             for (int d = 1; d < LPR; d <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
@@ -882,6 +887,7 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             // Every consumer warp walks every stage of the segment (the empty barriers count NWC arrivals); a warp whose pair lies past
             // the end of a ragged last stage just releases it.  Two stages per trip, ping-pong: while the gathers of one position run,
             // the words (and x) of the next are already on their way from shared memory into the other register set.
+#if SQLLM_V2_PIPE
             Fetch<BITS, XH> F0, F1;
             int k = 0, sl0, sl1;
             mbar_wait(bar_u32 + 8 * slot, par);
@@ -912,6 +918,23 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
                 k += 2;
                 xaddr += 2 * XBS;
             }
+#else
+            // one stage per trip, no look-ahead: the smallest loop body.  (The two-stage ping-pong variant above hides the word fetch
+            // behind the previous position's gathers but doubles the body to ~290 instructions; with 23 warps in five roles on the SM
+            // the instruction cache misses ate the gain - ncu: 18 % of the stall samples "no instruction" - see profiles/r02_*.)
+            for (int k = 0; k < nstg; ++k) {
+                mbar_wait(bar_u32 + 8 * slot, par);
+                if (k < mine) {
+                    Fetch<BITS, XH> F;
+                    fetch2<BITS, XH>(F, stage_of(slot), xaddr);
+                    math2<BITS, MODE, XH>(F, jsel, l, segc, xaddr, A);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_u32 + 128 + 8 * slot);
+                advance();
+                xaddr += XBS;
+            }
+#endif
             {   // this strip's sums: lane (i, j=1) holds column t^1 in slot t - hand it to lane (i, j=0), which adds both into the CTA's
                 // shared accumulator of the strip (16 warps x 64 red.shared.add; the builders move it on to global memory)
                 float s[4];

@@ -129,8 +129,16 @@ def main():
             for L, y in zip(Ls, ys):
                 call12(ref, L, x32, y)
 
+        def ours_fused_lut16():
+            qc.set_lut_mode("fp16")
+            try:
+                ours_fused()
+            finally:
+                qc.set_lut_mode("exact")
+
         res = []
-        for name, fn, graph in (("ours_accumulate", ours_acc, True), ("ours_fused_fp16", ours_fused, True), ("reference_kernel", theirs, False)):
+        for name, fn, graph in (("ours_accumulate", ours_acc, True), ("ours_fused_fp16", ours_fused, True), ("ours_fused_fp16_lut16", ours_fused_lut16, True),
+                                ("reference_kernel", theirs, False)):
             if fn is theirs and (ref is None or K % 128 or N % 128):
                 continue
             ms = time_loop(fn, 10, graph)
@@ -140,5 +148,38 @@ def main():
             print(json.dumps(res[-1]), flush=True)
 
 
+def batched():
+    """The *_batched symbols (prefill-shaped inputs): ours (register-tiled LUT GEMM + batched outlier kernels)
+    against the reference's own batched kernels on the same GPU, eager launches on both sides, B rows of a 4096 x 4096 layer."""
+    ref = build_ref.load() if build_ref.have_ref_so() else None
+    for bits, K, N, sp, topx in [(4, 4096, 4096, 0.0, 0), (4, 4096, 4096, 0.0045, 10), (3, 4096, 4096, 0.0045, 10)]:
+        L = synth(bits, K, N, sp, topx, 1)[0]
+        for B in (16, 64, 2048):
+            x = torch.randn((B, K), device="cuda").half().float()
+            out = {}
+            for name, mod in (("ours_batched", qc), ("reference_batched", ref)):
+                if mod is None:
+                    continue
+                y = torch.zeros((B, N), device="cuda")
+
+                def fn():
+                    b = L["bits"]
+                    if "rows" in L and "full_rows" in L:
+                        getattr(mod, f"vecquant{b}matmul_spmv_hybrid_nuq_perchannel_batched")(L["rows"], L["cols"], L["vals"], x, L["full_rows"], L["fri"], y, N, L["qweight"], L["lut"])
+                    elif "rows" in L:
+                        getattr(mod, f"vecquant{b}matmul_spmv_nuq_perchannel_batched")(L["rows"], L["cols"], L["vals"], x, y, N, L["qweight"], L["lut"])
+                    else:
+                        getattr(mod, f"vecquant{b}matmul_nuq_perchannel_batched")(x, L["qweight"], y, L["lut"])
+                out[name] = time_loop(fn, 5, False)
+            rec = dict(kind="batched", bits=bits, K=K, N=N, sparsity=sp, topX=topx, batch=B, ours_ms=round(out["ours_batched"], 4),
+                       ours_tflops=round(2.0 * B * K * N / out["ours_batched"] / 1e9, 2))
+            if "reference_batched" in out:
+                rec.update(reference_ms=round(out["reference_batched"], 4), speedup=round(out["reference_batched"] / out["ours_batched"], 2))
+            print(json.dumps(rec), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--batched":
+        batched()
+    else:
+        main()

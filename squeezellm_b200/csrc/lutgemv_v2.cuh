@@ -21,6 +21,9 @@
 //   * x is staged whole (as fp16 when it is given as fp16), the sparse warps gather it from shared memory.
 #pragma once
 
+#ifndef SQLLM_CSR_LOCAL
+#define SQLLM_CSR_LOCAL 0   // 1: a CTA sums the CSR rows of the strips it owns, in shared memory; 0: rows spread evenly over all CTAs (see sparse2)
+#endif
 #ifndef SQLLM_V2_PIPE
 #define SQLLM_V2_PIPE 0   // 1: two-stage ping-pong word fetch in the consumer loop (measured, not faster: see the loop)
 #endif
@@ -354,7 +357,7 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
     // The CTA's rows [ca, cb) are split over its NSPW sparse warps (warp 0, which also has the dense rows, takes half a share).
     int ca = 0, cb = 0;
     if (p.rows) {
-        if constexpr (FUSED) {
+        if constexpr (FUSED && SQLLM_CSR_LOCAL) {
             const long long cb0 = (long long)blockIdx.x * p.chunk, cb1 = min((long long)p.T, cb0 + p.chunk);
             ca = min(N, (int)((cb0 + p.R - 1) / p.R) * STRIP);
             cb = min(N, (int)((cb1 + p.R - 1) / p.R) * STRIP);
@@ -370,14 +373,15 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
         rb = spw == 0 ? ca + w0 : ca + w0 + (int)((long long)rest * spw / (NSPW - 1));
     }
     const int nr = rb - r;
-    const bool local_sums = FUSED && cb - ca <= SP_ROWS;  // the CTA's row pointers and row sums live in shared memory (same rule in the builders)
+    const bool rows_in_smem = cb - ca <= SP_ROWS;                       // the CTA's row pointers live in shared memory
+    const bool local_sums = FUSED && SQLLM_CSR_LOCAL && rows_in_smem;  // ... and so do the row sums (same rule in the builders)
     auto emit = [&](int row, float v) {
         if (local_sums) srowacc[row - ca] += v;  // plain read-modify-write: a row belongs to this warp alone and its pieces arrive one after the other
         else atomicAdd(acc_out + row, v);
     };
     int e_lo = 0, e_hi = 0;
     if (nr > 0) {
-        if (local_sums)
+        if (rows_in_smem)
             for (int i = lane; i <= nr; i += 32) {
                 srow[r - ca + i] = __ldg(p.rows + r + i);   // (the boundary entry is written by both neighbours, with the same value)
                 if (i < nr) srowacc[r - ca + i] = 0.f;
@@ -453,7 +457,7 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
                 if (c >= 0 && c < N) atomicAdd(acc_out + c, a);
             }
         }
-        if constexpr (FUSED) {
+        if constexpr (FUSED && SQLLM_CSR_LOCAL) {
             // announce this CTA's dense-row contributions now, early in the kernel: one fence, then a relaxed increment per distinct
             // strip that holds a dense-row channel (every one of the hc contributing CTAs does this; the owners expect hc arrivals)
             __threadfence();
@@ -505,8 +509,8 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
             const int row = rcur + lane / LPR, part = lane & (LPR - 1);
             int a0 = e_hi, a1 = e_hi;
             if (row < rb) {
-                a0 = local_sums ? srow[row - ca] : __ldg(p.rows + row);
-                a1 = local_sums ? srow[row - ca + 1] : __ldg(p.rows + row + 1);
+                a0 = rows_in_smem ? srow[row - ca] : __ldg(p.rows + row);
+                a1 = rows_in_smem ? srow[row - ca + 1] : __ldg(p.rows + row + 1);
             }
             const bool inter = row < rb && a0 < t1;
             const int s0 = max(a0, f0) - t0, s1 = min(a1, t1) - t0;
@@ -541,9 +545,33 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
         __syncwarp();
         stage_chunk(ci + 2);  // this buffer is free again
     }
-    if constexpr (FUSED) {
+    if constexpr (FUSED && SQLLM_CSR_LOCAL) {
         if (!local_sums && cb > ca) __threadfence();  // (more owned rows than the row accumulator holds: sums went to global memory)
         named_bar_sync(4, (NSPW + NBW) * 32);         // hand-over to the builders: row sums complete
+    } else if constexpr (FUSED) {
+        // Balanced mode: this CTA's outlier sums went to the global accumulator with red.add.  Announce them: all sparse warps meet,
+        // then ONE fence (by warp 0) and a relaxed increment per strip the CTA's rows touch (whatever their nnz) and per distinct
+        // strip that holds a dense-row channel - the owners of those strips expect exactly these arrivals.
+        named_bar_sync(5, NSPW * 32);
+        if (spw == 0) {
+            __threadfence();
+            __syncwarp();
+            int *flags = p.ws_cnt + 64;
+            if (cb > ca)
+                for (int s = ca / STRIP + lane; s <= (cb - 1) / STRIP; s += 32)
+                    asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(flags + s) : "memory");
+            if (p.full_rows && (int)blockIdx.x < p.hc)
+                for (int j = lane; j < p.topX; j += 32) {
+                    const int c = __ldg(p.fri + j);
+                    if (c < 0 || c >= N) continue;
+                    bool seen = false;
+                    for (int j2 = 0; j2 < j; ++j2) {
+                        const int c2 = __ldg(p.fri + j2);
+                        seen |= (c2 >= 0 && c2 < N && c2 / STRIP == c / STRIP);
+                    }
+                    if (!seen) asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(flags + c / STRIP) : "memory");
+                }
+        }
     }
 }
 
@@ -714,6 +742,10 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             for (int i = bt; i < nown; i += NBT) {
                 const int strip = so0 + i;
                 int expect = (int)((((long long)strip + 1) * R - 1) / p.chunk) - (int)blockIdx.x;  // dense CTAs after this one
+                if (!SQLLM_CSR_LOCAL && p.rows) {  // every CTA whose share of the CSR rows touches the strip
+                    const int c0 = strip * STRIP, c1 = min(N, c0 + STRIP) - 1;
+                    expect += c1 / p.csr_rpc - c0 / p.csr_rpc + 1;
+                }
                 if (p.full_rows) {
                     bool h = false;
                     for (int j = 0; j < p.topX; ++j) {
@@ -738,7 +770,7 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             }
             named_bar_sync(3, NBT);  // the polls above are through: the others' contributions to every owned strip are complete
             const float *srowacc = reinterpret_cast<const float *>(sm + OFF_SROW + (SP_ROWS + 1) * 4);
-            const bool local_sums = p.rows && min(N, so1 * STRIP) - min(N, so0 * STRIP) <= SP_ROWS;  // same rule as the sparse warps'
+            const bool local_sums = SQLLM_CSR_LOCAL && p.rows && min(N, so1 * STRIP) - min(N, so0 * STRIP) <= SP_ROWS;  // same rule as the sparse warps'
             const int w = p.xw_world ? N / p.xw_members : 0;
             auto store_y = [&](int col, float yv) {
                 if (local_sums) yv += srowacc[col - so0 * STRIP];
@@ -771,7 +803,7 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             float pre = 0.f;
             const int lcol = (s0 + nseg - 1) * STRIP + bt;
             if (last_owned && nseg > 0 && lcol < N) pre = __ldcg(p.ws_acc + lcol);
-            named_bar_sync(4, (NSPW + NBW) * 32);  // this CTA's own outlier row sums (sparse warps) are complete
+            if (SQLLM_CSR_LOCAL) named_bar_sync(4, (NSPW + NBW) * 32);  // this CTA's own outlier row sums (sparse warps) are complete
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int col = (so0 + u) * STRIP + bt;

@@ -78,7 +78,10 @@ constexpr int HYB_R = 11;                 // dense rows: k-rows per lane slot re
 constexpr int MAX_STRIPS = 16320;         // per-strip tickets in the workspace header (out_features <= 1,044,480)
 constexpr int MAX_N_FUSED = 262144;        // fused path: the scratch accumulator lives at a fixed place in the workspace
 constexpr size_t WS_ACC_OFF = 65536;       // [64 KB, 64 KB + 4*MAX_N_FUSED): fp32 accumulator (zero between launches)
-constexpr size_t WS_HEADER = WS_ACC_OFF + (size_t)MAX_N_FUSED * 4;  // tickets + accumulator: never shared with data of any shape
+constexpr int MAX_GRID_V2 = 256;           // v2 runs one CTA per SM
+constexpr size_t WS_HBOX_OFF = WS_ACC_OFF + (size_t)MAX_N_FUSED * 4;       // v2 mailboxes: [MAX_GRID_V2][64] x 8 bytes (partial strip sums)
+constexpr size_t WS_CBOX_OFF = WS_HBOX_OFF + (size_t)MAX_GRID_V2 * 64 * 8;  // ... and [MAX_N_FUSED] x 8 bytes (outlier row sums); zero between launches
+constexpr size_t WS_HEADER = WS_CBOX_OFF + (size_t)MAX_N_FUSED * 8;  // tickets + accumulator + mailboxes: never shared with data of any shape
 constexpr int MAX_NSTAGE = 16;            // weight stages per CTA (runtime count, fills the shared-memory budget)
 
 struct Params {
@@ -1679,6 +1682,7 @@ int make_plan2(int bits, int K, int N, int topX, int variant, bool fused, Plan2 
     if (chunk < 2) chunk = 2;
     pl.chunk = chunk;
     pl.G = (int)((T + chunk - 1) / chunk);
+    if (fused && pl.G > MAX_GRID_V2) return fail(SQLLM_EINVAL, "grid of %d CTAs exceeds the mailbox area (%d)", pl.G, MAX_GRID_V2);
     // shared memory, exactly as lutgemv2_kernel carves it: [fixed][x][ring stages ...][table 0][table 1][... ring stages]
     const unsigned raw = smem_raw;
     const unsigned base = (raw + 127u) & ~127u;
@@ -1738,6 +1742,12 @@ int launch2(const sqllm_lutgemv_args *a, int variant, bool fused, v2::P2 &p, cud
             const char *e = getenv("SQLLM_NO_PDL");
             g_use_pdl = (e && e[0] == '1') ? 0 : 1;
         }
+        static int l2pf = -1;
+        if (l2pf < 0) {
+            const char *e = getenv("SQLLM_L2PF");
+            l2pf = e ? (e[0] == '1') : 0;
+        }
+        p.l2pf = l2pf;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1916,6 +1926,8 @@ int sqllm_lutgemv_fused(const sqllm_lutgemv_args *a, const void *x, int x_is_hal
         memset(&q, 0, sizeof(q));
         q.ws_cnt = reinterpret_cast<int *>(ws);
         q.ws_acc = reinterpret_cast<float *>(ws + WS_ACC_OFF);
+        q.ws_hbox = reinterpret_cast<unsigned long long *>(ws + WS_HBOX_OFF);
+        q.ws_cbox = reinterpret_cast<unsigned long long *>(ws + WS_CBOX_OFF);
         q.x = x; q.out = y; q.y_is_half = y_is_half; q.bias = bias;
         return launch2(a, x_is_half ? (lut_mode() == 1 ? 2 : 1) : 0, true, q, static_cast<cudaStream_t>(stream));
     }
@@ -1962,6 +1974,8 @@ int sqllm_lutgemv_fused_exchange(const sqllm_lutgemv_args *a, const void *x, int
         memset(&q, 0, sizeof(q));
         q.ws_cnt = reinterpret_cast<int *>(ws);
         q.ws_acc = reinterpret_cast<float *>(ws + WS_ACC_OFF);
+        q.ws_hbox = reinterpret_cast<unsigned long long *>(ws + WS_HBOX_OFF);
+        q.ws_cbox = reinterpret_cast<unsigned long long *>(ws + WS_CBOX_OFF);
         q.x = x; q.out = nullptr; q.y_is_half = y_is_half; q.bias = bias;
         q.xw_world = xc->world; q.xw_rank = xc->rank; q.xw_members = xc->members; q.xw_nfull = xc->out_features_full;
         q.xw_base = reinterpret_cast<const unsigned long long *>(xc->peer_base);

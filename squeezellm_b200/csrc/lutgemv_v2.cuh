@@ -24,6 +24,9 @@
 #ifndef SQLLM_CSR_LOCAL
 #define SQLLM_CSR_LOCAL 0   // 1: a CTA sums the CSR rows of the strips it owns, in shared memory; 0: rows spread evenly over all CTAs (see sparse2)
 #endif
+#ifndef SQLLM_BOX
+#define SQLLM_BOX 1         // 1: contributions to another CTA's strip travel as self-validating {value, valid} words (see "mailboxes" below); 0: red.add + flags
+#endif
 #ifndef SQLLM_V2_PIPE
 #define SQLLM_V2_PIPE 0   // 1: two-stage ping-pong word fetch in the consumer loop (measured, not faster: see the loop)
 #endif
@@ -53,7 +56,7 @@ constexpr int OFF_SACC = 512;                   // float [2][64]: per-strip sums
 constexpr int OFF_CSR = OFF_SACC + 2 * STRIP * 4;            // per sparse warp: 2 x {int cols[SP_CH], float vals[SP_CH]}
 constexpr int OFF_SROW = OFF_CSR + NSPW * SP_BYTES;          // CTA-wide: int srow[SP_ROWS + 1], float srowacc[SP_ROWS + 1]
 constexpr int OFF_LUT = OFF_SROW + 2 * (SP_ROWS + 1) * 4;        // 2 x raw fp32 LUT rows of a strip (64 columns x 16 values), staged ahead by the builders
-constexpr int LUTBUF = STRIP * 16 * 4;
+constexpr int LUTBUF = STRIP * (16 * 4 + 16);                // a strip's raw LUT rows, one per column SLOT, row stride L*4 + 16 bytes (see lut_prefetch)
 constexpr int OFF_X = OFF_LUT + 2 * LUTBUF;                  // x (fp16 or fp32), then [ring stages][table 0][table 1][ring stages]
 static_assert(OFF_X % 128 == 0, "x must stay 128-byte aligned");
 
@@ -72,12 +75,15 @@ struct P2 {
     int y_is_half;
     int hc, hrows, csr_rpc, csr_al16;
     float *ws_acc;       // fused: [N] fp32 accumulator, zero between launches
+    unsigned long long *ws_hbox;  // fused, SQLLM_BOX: [grid][64] partial strip sums of a CTA's first segment when the strip starts in an earlier CTA
+    unsigned long long *ws_cbox;  // fused, SQLLM_BOX: [N] outlier (CSR) row sums; both {float value, u32 valid}, all zero between launches
     int *ws_cnt;         // fused: [16] error flag (a bounded wait gave up; sqllm_workspace_error), [64 + s] arrivals on strip s (zero between launches)
     int strips;          // output strips of 64 columns
     int nown_ctas;       // exchange: CTAs that own at least one strip (each announces itself once on every rank)
     int xw_world, xw_rank, xw_members, xw_nfull;
     const unsigned long long *xw_base;
     unsigned long long xw_out_off, xw_flag_off, xw_state_off, xw_err_off;
+    int l2pf;  // 1: prefetch the CTA's chunk of weights into L2 at entry
     unsigned long long *trace;
 };
 
@@ -123,15 +129,56 @@ __device__ __forceinline__ uint32_t f32x2_to_half2(float lo, float hi) {
 // in shared memory first (lut_prefetch, zero-filled past N): a build never waits on global memory, and it runs in the background -
 // the consumers only ever wait on an mbarrier that is normally long complete.  (First v2 build: the consumers rebuilt the table
 // themselves at every strip boundary; ncu showed 24 % of all stall samples on the LUT loads and a 0.8 / 2.3 us bubble per switch.)
+// ---------------------------------------------------------------------------------------------------------------------------
+// Mailboxes (fused mode, SQLLM_BOX).  A sum that one CTA produces and another CTA needs - the partial strip sums of a CTA whose first
+// segment continues a strip started earlier, and every outlier row sum (the CSR rows are spread evenly over the CTAs) - is written
+// ONCE, as one 64-bit word {fp32 value, valid = 1}, and the strip's owner polls that word.  A 64-bit access is single-copy atomic, so
+// the value needs no fence and no separate flag: the word validates itself.  Before: red.add into the accumulator, MEMBAR, flag
+// increment on the producer; acquire-poll of the flag, then a second round trip for the accumulator on the owner - three L2 round
+// trips (~2.5 us under load) between the last weight of a launch and its last y, now one.  The owner writes the word back to zero
+// (next launch's producers only write after the grid dependency resolved).  Only the dense-row sums, which have several producers
+// per channel, still go through red.add + flag; they are announced in the first microsecond of the kernel.
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long box_word(float v) { return (1ull << 32) | (unsigned long long)__float_as_uint(v); }
+// value of a mailbox word read speculatively as `w`; spins (bounded: 2 s, then the workspace error word) until it is valid; clears it
+__device__ __forceinline__ float box_take(unsigned long long w, unsigned long long *ptr, int *err) {
+    if (!(w >> 32)) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            w = ld_relaxed_u64(ptr);
+            if (w >> 32) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) { *reinterpret_cast<volatile int *>(err) = 1; break; }
+        } while (true);
+    }
+    st_relaxed_u64(ptr, 0ull);
+    return __uint_as_float((uint32_t)w);
+}
+
+// Staging layout: the row of column c sits at slot(c) * (L*4 + 16) bytes.  The builders read it with 16-byte loads, lane = slot: with the
+// rows packed by column (stride 4 columns x 64 B = 256 B between adjacent lanes) every LDS.128 was an 8-way bank conflict, and the
+// pair-table build re-reads the row for each of its 16 outer steps - ncu: 1.18 M of the fp16 kernel's 3.69 M shared-memory wavefronts
+// were these conflicts (profiles/r02_ncu_fp16_bank_conflicts.txt), as much LSU time as a third of the gathers.  With an 80-byte
+// (4-bit) / 48-byte (3-bit) stride the 8 lanes of each 128-byte phase cover all 32 banks.
 template <int BITS>
 __device__ __forceinline__ void lut_prefetch(const P2 &p, const uint32_t lutbuf, const int strip, const int bt) {
     constexpr int L = 1 << BITS;
     constexpr int N16 = STRIP * L / 4;  // 16-byte pieces: 256 (w4) / 128 (w3)
 #pragma unroll
     for (int e = bt; e < N16; e += NBT) {
-        const int col = strip * STRIP + e / (L / 4);
+        const int c = e / (L / 4), q = e % (L / 4), col = strip * STRIP + c;
+        const int slot = ((c & 3) << 4) | (c >> 2);
         const bool ok = col < p.N;
-        cp_async16_clip(lutbuf + 16 * e, p.lut + (ok ? (size_t)strip * STRIP * L + 4 * (size_t)e : 0), ok ? 16 : 0);
+        cp_async16_clip(lutbuf + slot * (L * 4 + 16) + 16 * q, p.lut + (ok ? (size_t)strip * STRIP * L + 4 * (size_t)e : 0), ok ? 16 : 0);
     }
     cp_async_commit();
 }
@@ -139,8 +186,7 @@ __device__ __forceinline__ void lut_prefetch(const P2 &p, const uint32_t lutbuf,
 template <int BITS, int MODE>
 __device__ __forceinline__ void build_table(const uint32_t tab, const uint32_t lutbuf, const int slot) {
     using C = C2<BITS, MODE>;
-    const int c = ((slot & 15) << 2) | (slot >> 4);          // the column this slot serves
-    const uint32_t row = lutbuf + c * C::L * 4;
+    const uint32_t row = lutbuf + slot * (C::L * 4 + 16);    // the staged LUT row of the column this slot serves (slot s <-> column (s & 15) * 4 + (s >> 4))
     const uint32_t a0 = tab + (slot << 2);                   // a warp's 32 lanes = 32 consecutive slots: conflict-free stores
     float v[C::L];
 #pragma unroll
@@ -375,8 +421,11 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
     const int nr = rb - r;
     const bool rows_in_smem = cb - ca <= SP_ROWS;                       // the CTA's row pointers live in shared memory
     const bool local_sums = FUSED && SQLLM_CSR_LOCAL && rows_in_smem;  // ... and so do the row sums (same rule in the builders)
+    constexpr bool BOX = FUSED && SQLLM_BOX && !SQLLM_CSR_LOCAL;  // row sums are published as mailbox words when the warp is through
+    const bool smem_sums = local_sums || (BOX && rows_in_smem);
     auto emit = [&](int row, float v) {
-        if (local_sums) srowacc[row - ca] += v;  // plain read-modify-write: a row belongs to this warp alone and its pieces arrive one after the other
+        if (smem_sums) srowacc[row - ca] += v;  // plain read-modify-write: a row belongs to this warp alone and its pieces arrive one after the other
+        else if (BOX) atomicAdd(reinterpret_cast<float *>(p.ws_cbox + row), v);  // (more rows per CTA than the shared accumulator holds: value half of the word)
         else atomicAdd(acc_out + row, v);
     };
     int e_lo = 0, e_hi = 0;
@@ -457,7 +506,7 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
                 if (c >= 0 && c < N) atomicAdd(acc_out + c, a);
             }
         }
-        if constexpr (FUSED && SQLLM_CSR_LOCAL) {
+        if constexpr (FUSED && (SQLLM_CSR_LOCAL || SQLLM_BOX)) {
             // announce this CTA's dense-row contributions now, early in the kernel: one fence, then a relaxed increment per distinct
             // strip that holds a dense-row channel (every one of the hc contributing CTAs does this; the owners expect hc arrivals)
             __threadfence();
@@ -548,6 +597,15 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
     if constexpr (FUSED && SQLLM_CSR_LOCAL) {
         if (!local_sums && cb > ca) __threadfence();  // (more owned rows than the row accumulator holds: sums went to global memory)
         named_bar_sync(4, (NSPW + NBW) * 32);         // hand-over to the builders: row sums complete
+    } else if constexpr (BOX) {
+        // every row of this warp's share gets its word, outlier-free rows included (the owner of the strip waits for all 64 of them)
+        __syncwarp();
+        if (smem_sums) {
+            for (int i = lane; i < nr; i += 32) st_relaxed_u64(p.ws_cbox + r + i, box_word(srowacc[r - ca + i]));
+        } else if (nr > 0) {
+            __threadfence();  // the red.adds on the value halves come first
+            for (int i = lane; i < nr; i += 32) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t *>(p.ws_cbox + r + i) + 1), "r"(1u) : "memory");
+        }
     } else if constexpr (FUSED) {
         // Balanced mode: this CTA's outlier sums went to the global accumulator with red.add.  Announce them: all sparse warps meet,
         // then ONE fence (by warp 0) and a relaxed increment per strip the CTA's rows touch (whatever their nnz) and per distinct
@@ -625,6 +683,17 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_big)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_small)) : "memory");
         }
+        if (p.l2pf) {
+            // the CTA's whole chunk of weights -> L2, one box per lane and instruction, before the dependency wait: the ring then only has
+            // to cover L2 latency, and under PDL these requests overlap the previous kernel's tail
+            for (int seg = 0; seg < nseg; ++seg) {
+                const int sstart = seg == 0 ? 0 : seg * R - r0, send = min(len, (seg + 1) * R - r0);
+                const int u0 = r0 + sstart - seg * R, col0 = (s0 + seg) * STRIP;
+                for (int u = lane * SU2; u < send - sstart; u += 32 * SU2)
+                    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(&tm_big)),
+                                 "r"(col0), "r"((u0 + u) * C::ROWS) : "memory");
+            }
+        }
         const int G = (int)gridDim.x;
         const size_t lut_lines = ((size_t)N * C::L * 4 + 127) / 128, per = (lut_lines + G - 1) / G;
         for (size_t i = (size_t)blockIdx.x * per + lane; i < min(lut_lines, ((size_t)blockIdx.x + 1) * per); i += 32)
@@ -691,13 +760,19 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             const float v = lds_f32(a);
             sts_u32(a, 0u);
             const int strip = s0 + s, col = strip * STRIP + bt;
-            if (col < N) atomicAdd(acc_out + col, v);
-            if constexpr (FUSED) {
+            if constexpr (FUSED && SQLLM_BOX && !SQLLM_CSR_LOCAL) {
                 // A strip is finished (converted to y) by the CTA in whose range it STARTS; a CTA that only holds a later part of it
-                // (that can only be its first segment) announces its contribution on the strip's flag.
-                if (s == 0 && r0 != 0) {
-                    named_bar_sync(3, NBT);
-                    if (bt == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + strip) : "memory");
+                // (that can only be its first segment) hands its sums to that owner through its mailbox row.
+                if (s == 0 && r0 != 0) st_relaxed_u64(p.ws_hbox + (size_t)blockIdx.x * STRIP + bt, box_word(v));
+                else if (col < N) atomicAdd(acc_out + col, v);
+            } else {
+                if (col < N) atomicAdd(acc_out + col, v);
+                if constexpr (FUSED) {
+                    // (flag protocol) ... announces its contribution on the strip's flag
+                    if (s == 0 && r0 != 0) {
+                        named_bar_sync(3, NBT);
+                        if (bt == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + strip) : "memory");
+                    }
                 }
             }
         };
@@ -739,6 +814,116 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             const long long cb0 = (long long)blockIdx.x * p.chunk, cb1 = min((long long)p.T, cb0 + p.chunk);
             const int so0 = (int)((cb0 + R - 1) / R), so1 = (int)((cb1 + R - 1) / R), nown = so1 - so0;
             const bool last_owned = nseg >= 2 || r0 == 0;  // the last segment's strip starts in this CTA's range (it is strip so1 - 1)
+#if SQLLM_BOX && !SQLLM_CSR_LOCAL
+            // ---- mailbox variant.  Thread bt owns column bt of every owned strip.  What it adds up per column:
+            //        the accumulator   - this CTA's own sums of the strip unless it is the last segment's (those never leave shared memory),
+            //                            plus the dense-row sums if a dense-row channel lies in the strip (flag: hc arrivals, early in the kernel)
+            //        cbox[col]         - the column's outlier sum, from whichever CTA has that CSR row
+            //        hbox[b+1..b+nh]   - last owned strip only: the later CTAs' parts of it
+            //      All words are requested at once, speculatively, while the consumers are in the last segment; box_take spins on the few
+            //      that were not there yet.
+            {
+                constexpr int FAST = 4;  // owned strips handled from registers (7B..65B shapes own <= 4)
+                int *const err = p.ws_cnt + 16;
+                const int lidx = last_owned && nseg > 0 ? nown - 1 : -1;  // index of the last segment's strip among the owned ones
+                const int nh = lidx >= 0 ? (int)((((long long)(so1 - 1) + 1) * R - 1) / p.chunk) - (int)blockIdx.x : 0;
+                unsigned long long cw[FAST], hw[3];
+#pragma unroll
+                for (int u = 0; u < FAST; ++u) {
+                    const int col = (so0 + u) * STRIP + bt;
+                    cw[u] = (p.rows && u < nown && col < N) ? ld_relaxed_u64(p.ws_cbox + col) : box_word(0.f);
+                }
+#pragma unroll
+                for (int h = 0; h < 3; ++h)
+                    hw[h] = h < nh ? ld_relaxed_u64(p.ws_hbox + ((size_t)blockIdx.x + 1 + h) * STRIP + bt) : box_word(0.f);
+                if (p.full_rows) {  // dense rows: strips with a channel wait for the hc early announcements
+                    for (int i = bt; i < nown; i += NBT) {
+                        const int strip = so0 + i;
+                        bool hch = false;
+                        for (int j = 0; j < p.topX; ++j) {
+                            const int c = __ldg(p.fri + j);
+                            hch |= (c >= 0 && c < N && c / STRIP == strip);
+                        }
+                        if (hch) {
+                            int seen;
+                            unsigned long long t0 = 0ull, t1;
+                            do {
+                                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + strip) : "memory");
+                                if (seen >= p.hc) break;
+                                __nanosleep(40);
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                                if (t0 == 0ull) t0 = t1;
+                                if (t1 - t0 > 2000000000ull) { *reinterpret_cast<volatile int *>(err) = 1; break; }
+                            } while (true);
+                            flags[strip] = 0;
+                        }
+                    }
+                    named_bar_sync(3, NBT);
+                }
+                const int w = p.xw_world ? N / p.xw_members : 0;
+                auto store_y = [&](int col, float yv) {
+                    if (p.bias) yv += __ldg(p.bias + col);
+                    if (p.xw_world == 0) {
+                        if (p.y_is_half) reinterpret_cast<__half *>(p.out)[col] = __float2half_rn(yv);
+                        else reinterpret_cast<float *>(p.out)[col] = yv;
+                    } else {
+                        // local column col of the stacked shard = column j of member m; it lands at [m][rank*w + j] of the
+                        // [members][n_full] vector in EVERY rank's arena
+                        const int mm = col / w, j = col - mm * w;
+                        const unsigned long long e = (unsigned long long)mm * p.xw_nfull + (unsigned long long)p.xw_rank * w + j;
+                        for (int pr = 0; pr < p.xw_world; ++pr) {
+                            unsigned char *dst = reinterpret_cast<unsigned char *>(__ldg(p.xw_base + pr) + p.xw_out_off);
+                            if (p.y_is_half) *reinterpret_cast<__half *>(dst + 2 * e) = __float2half_rn(yv);
+                            else *reinterpret_cast<float *>(dst + 4 * e) = yv;
+                        }
+                    }
+                };
+                float av[FAST];  // accumulator values (zero where nothing was ever added: the array is zero between launches)
+#pragma unroll
+                for (int u = 0; u < FAST; ++u) {
+                    const int col = (so0 + u) * STRIP + bt;
+                    av[u] = (u < nown && col < N) ? __ldcg(p.ws_acc + col) : 0.f;
+                }
+                float last_others = 0.f;  // everything but this CTA's own sums of the last segment's strip
+#pragma unroll
+                for (int u = 0; u < FAST; ++u) {
+                    const int col = (so0 + u) * STRIP + bt;
+                    if (u < nown && col < N) {
+                        float yv = av[u];
+                        if (p.rows) yv += box_take(cw[u], p.ws_cbox + col, err);
+                        p.ws_acc[col] = 0.f;
+                        if (u == lidx) last_others = yv;
+                        else store_y(col, yv);
+                    }
+                }
+                for (int i = FAST; i < nown; ++i) {  // (more owned strips than FAST: one at a time)
+                    const int col = (so0 + i) * STRIP + bt;
+                    if (col < N) {
+                        float yv = __ldcg(p.ws_acc + col);
+                        if (p.rows) yv += box_take(0ull, p.ws_cbox + col, err);
+                        p.ws_acc[col] = 0.f;
+                        if (i == lidx) last_others = yv;
+                        else store_y(col, yv);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 3; ++h)
+                    if (h < nh) last_others += box_take(hw[h], p.ws_hbox + ((size_t)blockIdx.x + 1 + h) * STRIP + bt, err);
+                for (int h = 3; h < nh; ++h) last_others += box_take(0ull, p.ws_hbox + ((size_t)blockIdx.x + 1 + h) * STRIP + bt, err);
+                TRACE(8, bt == 0);
+                if (nseg > 0) {
+                    const int s = nseg - 1;
+                    mbar_wait(bar_u32 + 272 + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
+                    if (last_owned) {
+                        const float own = lds_f32(sacc + 4 * ((s & 1) * STRIP + bt));
+                        const int lcol = (s0 + s) * STRIP + bt;
+                        if (lcol < N) store_y(lcol, last_others + own);
+                    } else {
+                        flush(s);  // a CTA that lies wholly inside a strip started by another one: its mailbox row
+                    }
+                }
+            }
+#else
             for (int i = bt; i < nown; i += NBT) {
                 const int strip = so0 + i;
                 int expect = (int)((((long long)strip + 1) * R - 1) / p.chunk) - (int)blockIdx.x;  // dense CTAs after this one
@@ -832,6 +1017,7 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
                     flush(s);  // a CTA that lies wholly inside a strip started by another one: contribute and announce
                 }
             }
+#endif
             if (p.xw_world) {
                 // exchange: every owning CTA publishes its stores on every rank (system-scope release); CTA 0 (it always owns strip 0)
                 // then holds the grid open until every owning CTA of every rank has published on ours: when this grid completes, the
@@ -916,6 +1102,7 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             const int mine = 2 * warp < seglen ? (seglen - 2 * warp + SU2 - 1) / SU2 : 0;  // stages in which this warp has a pair
 
             mbar_wait(bar_u32 + 256 + 8 * b, (uint32_t)((seg >> 1) & 1));  // table b holds this strip
+            TRACE(16 + (seg < 7 ? seg : 7), tid == 0);
             // Every consumer warp walks every stage of the segment (the empty barriers count NWC arrivals); a warp whose pair lies past
             // the end of a ragged last stage just releases it.  Two stages per trip, ping-pong: while the gathers of one position run,
             // the words (and x) of the next are already on their way from shared memory into the other register set.
@@ -991,6 +1178,7 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_u32 + 272 + 8 * b);  // done with table b, sums deposited
             }
+            TRACE(24 + (seg < 7 ? seg : 7), tid == 0);
         }
         TRACE(6, tid == 0);
     }

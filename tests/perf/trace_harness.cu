@@ -104,18 +104,19 @@ int main(int argc, char **argv) {
         }
         printf("\n");
     }
-    {   // per-CTA detail of a steady-state launch: smid, post-wait, per-stage ready times, loop-end, relative to that launch's min post-wait
+    {   // per-CTA detail of a steady-state launch, relative to that launch's min post-wait.  v2 marks: 16+s = table of segment s ready,
+        // 24+s = segment s done; 8/9 = builders: polls through / y written; 10 = sparse warp 0 done
         const int i = chain - 2;
         unsigned long long base = ~0ull;
         for (int c = 0; c < G; ++c) { unsigned long long v = h[(size_t)i * stride + c * 32 + 3]; if (v) base = std::min(base, v); }
-        printf("launch %d per-CTA (us rel. to min post-wait): cta smid entry post-wait x-staged st0..st7 loop-end exit\n", i);
-        for (int c = 0; c < G; c += (G > 64 ? 7 : 1)) {
+        printf("launch %d per-CTA (us rel. to min post-wait): cta smid entry post-wait x-staged | tab0 seg0 tab1 seg1 tab2 seg2 | loop-end sparse polls y-done exit\n", i);
+        const int step = getenv("TRACE_ALL") ? 1 : (G > 64 ? 7 : 1);
+        for (int c = 0; c < G; c += step) {
             const unsigned long long *r = &h[(size_t)i * stride + c * 32];
             auto rel = [&](unsigned long long v) { return v ? ((double)v - (double)base) / 1e3 : -99.0; };
             printf("%4d %4d %7.2f %6.2f %6.2f |", c, (int)r[12] - 1, rel(r[0]), rel(r[3]), rel(r[4]));
-            printf(" %6.2f", rel(r[5]));
-            for (int s2 = 1; s2 < 8; ++s2) printf(" %6.2f", rel(r[16 + s2]));
-            printf(" | %6.2f %6.2f\n", rel(r[6]), rel(r[11]));
+            for (int s2 = 0; s2 < 3; ++s2) printf(" %6.2f %6.2f", rel(r[16 + s2]), rel(r[24 + s2]));
+            printf(" | %6.2f %6.2f %6.2f %6.2f %6.2f\n", rel(r[6]), rel(r[10]), rel(r[8]), rel(r[9]), rel(r[11]));
         }
     }
     return 0;

@@ -36,6 +36,8 @@ SHAPES = [  # (bits, K, N, sparsity, topX, nonzero_full_rows, skew)
     (3, 22016, 1024, 0.0045, 10, False, False), # 65B down, 1 of 8 column shards
     (4, 4096, 22016, 0.0045, 10, False, False), # 7B gate+up stacked (fusion.py)
     (4, 4096, 12288, 0.0045, 10, True, True),   # 7B q+k+v stacked, skewed outliers
+    (4, 256, 44032, 0.01, 4, True, False),      # more CSR rows per CTA than the shared row accumulator holds (mailbox fallback path)
+    (3, 11008, 64, 0.01, 4, True, False),       # one strip, every CTA inside it: 147 mailbox rows for one owner
 ]
 IDS = [f"w{b}-{k}x{n}-s{int(s*1e4)}-t{t}{'-nz' if z else ''}{'-skew' if sk else ''}" for b, k, n, s, t, z, sk in SHAPES]
 

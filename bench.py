@@ -184,6 +184,56 @@ def make_step(layers, world, peer=None):
     return step, run_layer
 
 
+def seq_record_layer(seq, L, x, world=1):
+    """Record the 7 matvecs of decoder layer L into the DecodeSequence `seq`, reading the SeqVec `x`; same wiring as make_step.
+    Returns [(name, input SeqVec, output SeqVec)] in model order."""
+    def stacked(names, xin):
+        g = L[names[0]]._sibling_group
+        if g is not None:
+            y = seq.matvec(g[0].layer, xin, members=len(names))
+            n = len(y) // len(names)
+            return [y[i * n:(i + 1) * n] for i in range(len(names))]
+        return [seq.matvec(L[n], xin) for n in names]
+    q, k, v = stacked(("q_proj", "k_proj", "v_proj"), x)
+    o = seq.matvec(L["o_proj"], v)
+    g, u = stacked(("gate_proj", "up_proj"), o)
+    d = seq.matvec(L["down_proj"], g)
+    return [("q_proj", x, q), ("k_proj", x, k), ("v_proj", x, v), ("o_proj", v, o), ("gate_proj", o, g), ("up_proj", o, u), ("down_proj", g, d)]
+
+
+def make_seq_step(layers, cfg, dev, mode, peer=None):
+    """The whole token as ONE persistent launch (squeezellm_b200.runtime.DecodeSequence): returns (sequence, step(x) -> x')."""
+    from squeezellm_b200.runtime import DecodeSequence
+    seq = DecodeSequence(cfg["hidden"], dev, lut_mode=mode, peer=peer)
+    x = seq.input
+    for L in layers:
+        x = seq_record_layer(seq, L, x, peer.world if peer is not None else 1)[-1][2]
+    seq.compile(outputs=[x])
+
+    def step(xin):
+        if xin is not seq.x:
+            seq.x.copy_(xin)
+        return seq.replay()[0]
+    return seq, step
+
+
+def make_seq_run_layer(cfg, dev, quant_cuda, peer=None):
+    """run_layer for parity_check: the sampled layer as a (one-layer) sequence, every matvec's full-length output exported."""
+    from squeezellm_b200.runtime import DecodeSequence
+
+    def run_layer(L, x):
+        seq = DecodeSequence(cfg["hidden"], dev, lut_mode=quant_cuda.get_lut_mode(), peer=peer)
+        rec = seq_record_layer(seq, L, seq.input, peer.world if peer is not None else 1)
+        seq.compile(outputs=[r[2] for r in rec] + [r[1] for r in rec if r[1].item >= 0])
+        seq.x.copy_(x)
+        outs = [o.clone() for o in seq.replay()]
+        torch.cuda.synchronize()
+        assert not seq.error(), "a bounded in-kernel wait of the sequence gave up"
+        ys, xs = outs[:len(rec)], iter(outs[len(rec):])
+        return [(r[0], x if r[1].item < 0 else next(xs), y) for r, y in zip(rec, ys)]
+    return run_layer
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # clocks during the timed region
 # ------------------------------------------------------------------------------------------------------------------
@@ -327,6 +377,9 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how column shards are reassembled - p2p: stores into every rank's symmetric arena from inside the GEMV "
                          "kernel (falls back to nccl if symmetric memory is unavailable or the self-check fails); nccl: one all-reduce per launch")
+    ap.add_argument("--launch", default="seq", choices=["seq", "graph"],
+                    help="seq (default, single GPU): the whole token as ONE persistent kernel launch (runtime.DecodeSequence, csrc/lutgemv_seq.cuh); "
+                         "graph: one launch per (stacked) matvec, chained with PDL inside a CUDA graph (round 1 / early round 2)")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinearLUT (no q/k/v and gate/up sibling stacking)")
     ap.add_argument("--lut", default="both", choices=["both", "exact", "fp16"],
                     help="codebook precision: exact = fp32 as stored (headline), fp16 = pair tables; both = headline exact + a lut_fp16 object")
@@ -409,6 +462,7 @@ def main():
                 print(f"[bench] rank {rank}: p2p exchange not used ({why or 'another rank declined'}); falling back to NCCL", file=sys.stderr)
     else:
         step, run_layer = make_step(layers, world)
+    use_seq = args.launch == "seq" and world == 1
     x0 = torch.randn(cfg["hidden"], device=dev).half()
 
     def barrier():
@@ -427,8 +481,14 @@ def main():
         The mode is baked into the graph at capture time (the kernel variant is chosen per launch)."""
         quant_cuda.set_lut_mode(lut_mode)
         graphed = True
+        seq = None
         try:
-            runner = GraphedDecodeStep(step, x0, warmup=3)
+            if use_seq:
+                seq, _ = make_seq_step(layers, cfg, dev, lut_mode)
+                seq.x.copy_(x0)
+                runner = GraphedDecodeStep(lambda x: seq.replay()[0], seq.x, warmup=3, static_input=True)
+            else:
+                runner = GraphedDecodeStep(step, x0, warmup=3)
         except Exception as e:  # e.g. NCCL refusing capture: fall back to eager launches, and say so
             if world == 1:
                 raise
@@ -484,6 +544,10 @@ def main():
             blocks, e2e_ms = t.tolist()[:-1], t.tolist()[-1]
         ms = statistics.median(blocks)
         quant_cuda.set_lut_mode("exact")
+        if seq is not None:
+            assert not seq.error(), "a bounded in-kernel wait of the sequence kernel gave up during the timed run: the numbers are void"
+            del runner, seq
+            torch.cuda.empty_cache()
         return {"ms_step": ms / args.steps, "e2e_ms_step": e2e_ms / args.steps, "blocks_ms": [round(b, 4) for b in blocks],
                 "graphed": graphed, "clocks": clocks}
 
@@ -541,6 +605,8 @@ def main():
     extra_run = measure("fp16", False) if args.lut == "both" else None
 
     # ---- parity: one sampled layer group per rank against the fp64 oracle on the same buffers (outside every timed region) ----------
+    if use_seq:
+        run_layer = make_seq_run_layer(cfg, dev, quant_cuda)
     parity = parity_check(layers, run_layer, cfg, rank, world, dev, quant_cuda)
     if world > 1:
         import torch.distributed as dist
@@ -579,23 +645,26 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
         except Exception:
             pass
-    kern = f"lutgemv2_kernel<{cfg['bits']}, {'fp16 pair table' if head_mode == 'fp16' else 'exact fp32 table'}, fused>"
+    kern = f"{'lutgemv_seq_kernel' if use_seq else 'lutgemv2_kernel'}<{cfg['bits']}, {'fp16 pair table' if head_mode == 'fp16' else 'exact fp32 table'}{'' if use_seq else ', fused'}>"
+    launches = 2 if use_seq else nlaunch  # seq: token counter + the persistent kernel
     out = {
         "metric": metric_name(args.workload),
         "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": ("f32 accumulate (fp16-rounded LUT x fp16 activations, exact products, fp16 outputs)" if head_mode == "fp16" else
                   "f32 accumulate (fp32 LUT x fp16->fp32 activations, fp16 outputs)"), "data": "synthetic",
-        "config": {**base_config(args, cfg), "launches_per_step": nlaunch,
+        "config": {**base_config(args, cfg), "launches_per_step": launches, "matvec_items_per_step": nlaunch,
                    "sibling_fusion": "q/k/v and gate/up stacked (squeezellm_b200.fusion)" if nlaunch != nmat else "off",
                    "l2": f"{nbytes_all / 1e9:.2f} GB of distinct weights per step >> 126 MB L2 (inputs larger than L2)",
                    "parallelism": "single GPU" if world == 1 else f"column-sharded x{world}, {nlaunch} launches per step", "exchange": exchange_used,
-                   "launch": "one CUDA-graph replay per step" if graphed else "eager launches (graph capture unavailable)",
+                   "launch": ("one CUDA-graph replay per step" if graphed else "eager launches (graph capture unavailable)") +
+                             (": ONE persistent kernel runs all matvecs of the token (runtime.DecodeSequence)" if use_seq else ": one PDL-chained launch per (stacked) matvec"),
                    "lut": head_mode, "timing": f"median of {args.blocks} blocks of {args.steps} steps", "layers_timed": cfg["layers"]},
         "blocks_ms": main_run["blocks_ms"],
         "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": cfg["hidden"] * 2, "d2h_bytes_per_step": cfg["hidden"] * 2,
-                "api": "squeezellm_b200.runtime.GraphedDecodeStep over QuantLinearLUT.forward" if graphed else "QuantLinearLUT.forward eager"},
-        "gpu_launches": nlaunch * args.steps,
+                "api": ("squeezellm_b200.runtime.GraphedDecodeStep over runtime.DecodeSequence (QuantLinearLUT modules)" if use_seq else
+                        "squeezellm_b200.runtime.GraphedDecodeStep over QuantLinearLUT.forward") if graphed else "QuantLinearLUT.forward eager"},
+        "gpu_launches": launches * args.steps,
         "clocks": main_run["clocks"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": kern,

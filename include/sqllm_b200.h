@@ -47,7 +47,7 @@ extern "C" {
 #define SQLLM_ECUDA (-2)    /* a CUDA runtime call or launch failed */
 #define SQLLM_EWORKSPACE (-3) /* workspace missing or too small */
 
-#define SQLLM_ABI_VERSION 3   /* 2: + sqllm_lutgemv_fused_exchange, sqllm_set_deterministic ; 3: + sqllm_set_lut_mode, sqllm_workspace_error */
+#define SQLLM_ABI_VERSION 4   /* 2: + sqllm_lutgemv_fused_exchange, sqllm_set_deterministic ; 3: + sqllm_set_lut_mode, sqllm_workspace_error ; 4: + sqllm_sequence_* */
 
 int sqllm_abi_version(void);
 const char *sqllm_last_error(void);
@@ -218,6 +218,56 @@ int sqllm_vecquant4matmul_spmv_hybrid_nuq_perchannel_batched(const int32_t *rows
                                                              const float *lookup_table, int height, int width,
                                                              int fr_height, int fr_width, int batch,
                                                              int vec_height, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sequences: ONE persistent launch for a whole list of dependent matvecs.
+ * Replaces the reference's per-layer launch loop during decode (squeezellm/llama.py:226-234 calls
+ * QuantLinearLUT.forward once per layer; each forward is quant.py:212-312, i.e. 1-3 launches of
+ * quant_cuda_kernel.cu:132-738).  Every item is one fused matvec (as sqllm_lutgemv_fused, fp16 in
+ * and out); its input is either an external fp16 vector or a slice of an earlier item's output.
+ * The kernel keeps the weight stream running across item boundaries and hands results from one
+ * item to the next as self-validating tagged words in an arena (csrc/lutgemv_seq.cuh) - no
+ * launch, no grid-wide barrier, no fence between two matvecs.  All items share `bits`.
+ *
+ * Several GPUs (column shards, one process per GPU): every rank creates the same sequence over
+ * its own shards (items[i].a.out_features = members * shard width) and passes the peer-visible
+ * arena of every rank; owners store their slice of each result into every rank's arena over
+ * NVLink, the next item's input poll is the exchange.  All ranks must call sqllm_sequence_run the
+ * same number of times.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sqllm_sequence sqllm_sequence;
+
+typedef struct sqllm_seq_item {
+    sqllm_lutgemv_args a;    /* the matrix: bits, in/out features, qweight, lookup_table, CSR, dense rows (vec/mul/batch ignored) */
+    const float *bias;       /* optional, [out_features] */
+    int x_from;              /* -1: x_ext ; i >= 0: the (full-length) output vector of item i < this item's index */
+    int x_offset;            /* first element of that vector this item reads (multiple of 4); it reads in_features elements */
+    const void *x_ext;       /* fp16 [in_features], read by every run (x_from == -1) */
+    void *y;                 /* optional plain fp16 [out_features] copy of this item's own output columns */
+    int members;             /* several GPUs: the item stacks `members` column shards of equal width (else 1) */
+    int out_features_full;   /* several GPUs: full length of one member's output vector (else out_features) */
+} sqllm_seq_item;
+
+typedef struct sqllm_seq_options {
+    int lut_mode;            /* SQLLM_LUT_EXACT / SQLLM_LUT_FP16_PAIR */
+    int world, rank;         /* 1, 0 on a single GPU */
+    void *arena;             /* world > 1: this rank's peer-visible arena (zero-filled once); NULL on one GPU: allocated here */
+    size_t arena_bytes;
+    const uint64_t *peer_base; /* world > 1: DEVICE array of `world` arena base addresses as seen from this rank */
+    int n_export;            /* results wanted as plain fp16 vectors: item indices and destinations (full length) */
+    const int *export_items;
+    void *const *export_dst;
+    uint64_t *trace;         /* debug builds (-DSQLLM_TRACE): [n_items][1024][32] time stamps, else NULL */
+} sqllm_seq_options;
+
+/* bytes of arena a sequence over these items needs (0 on error) */
+size_t sqllm_sequence_arena_bytes(const sqllm_seq_item *items, int n_items);
+int sqllm_sequence_create(const sqllm_seq_item *items, int n_items, const sqllm_seq_options *opt, sqllm_sequence **out);
+/* two launches on `stream` (token counter, then the persistent kernel); CUDA-graph capturable */
+int sqllm_sequence_run(sqllm_sequence *s, void *stream);
+/* synchronises `stream`; 1 if a bounded in-kernel wait ever gave up (results incomplete), 0 if not, < 0 on error */
+int sqllm_sequence_error(sqllm_sequence *s, void *stream);
+void sqllm_sequence_destroy(sqllm_sequence *s);
 
 /* Test hook: unpack the packed indices on the GPU exactly as the GEMV kernels do
  * (idx uint8 [in, out]); lets tests prove the integer path bit-exact on its own. */

@@ -43,7 +43,8 @@ def build_lib(verbose=False):
     src = os.path.join(CSRC, "lutgemv_kernels.cu")
     hdr = os.path.join(INCLUDE, "sqllm_b200.h")
     out = lib_path()
-    if _newer(out, [src, hdr, os.path.join(CSRC, "lutgemv_v2.cuh"), os.path.join(CSRC, "lutgemm_batched.cuh")]):
+    if _newer(out, [src, hdr, os.path.join(CSRC, "lutgemv_v2.cuh"), os.path.join(CSRC, "lutgemv_seq.cuh"),
+                    os.path.join(CSRC, "lutgemm_batched.cuh")]):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         cmd = [nvcc] + NVCC_FLAGS + ["-ccbin", _cxx(), "-I", INCLUDE, "-shared", "-o", out, src]
         if verbose:

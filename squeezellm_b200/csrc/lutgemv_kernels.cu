@@ -38,6 +38,7 @@
 #include <algorithm>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "sqllm_b200.h"
 
@@ -1278,6 +1279,7 @@ __global__ void unpack_kernel(int bits, const uint32_t *__restrict__ q, int K, i
 }
 
 #include "lutgemv_v2.cuh"
+#include "lutgemv_seq.cuh"
 #include "lutgemm_batched.cuh"
 
 // shared-window address at which a kernel without static shared memory sees its dynamic shared memory (the v2 carve-up aligns
@@ -1772,6 +1774,274 @@ int launch2(const sqllm_lutgemv_args *a, int variant, bool fused, v2::P2 &p, cud
     if (e != cudaSuccess) return fail(SQLLM_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return SQLLM_OK;
 }
+
+
+// ---- sequences (lutgemv_seq.cuh): plan + descriptors at create time, two launches per run -----------------------------
+typedef void (*KSeq)(const seq::SeqCfg);
+struct KSeqInfo { KSeq fn; int tab, stage, ntb; };
+KSeqInfo kseq_lookup(int bits, int mode, bool multi) {
+#define KSE(B, M, X) KSeqInfo{seq::lutgemv_seq_kernel<B, M, X>, v2::C2<B, M>::TAB, v2::C2<B, M>::STAGE, v2::C2<B, M>::TAB <= 16384 ? 4 : 2}
+    if (bits == 4) {
+        if (mode == 0) return multi ? KSE(4, 0, true) : KSE(4, 0, false);
+        return multi ? KSE(4, 1, true) : KSE(4, 1, false);
+    }
+    if (mode == 0) return multi ? KSE(3, 0, true) : KSE(3, 0, false);
+    return multi ? KSE(3, 1, true) : KSE(3, 1, false);
+#undef KSE
+}
+constexpr int SEQ_MAX_ITEMS = 1023;  // the mailbox tag keeps 10 bits for the item
+
+size_t seq_item_len(const sqllm_seq_item &it) {  // elements of the item's full-length output vector
+    const int members = it.members > 0 ? it.members : 1;
+    const int nfull = it.out_features_full > 0 ? it.out_features_full : it.a.out_features / members;
+    return (size_t)members * nfull;
+}
+}  // namespace
+
+struct sqllm_sequence {
+    int dev = 0, n = 0, bits = 0, mode = 0, world = 1, rank = 0, grid = 0, smem = 0, coop = 1;
+    seq::SeqCfg cfg;
+    KSeq fn = nullptr;
+    void *d_descs = nullptr, *d_exports = nullptr, *d_ws = nullptr, *d_arena = nullptr;
+    bool own_arena = false;
+};
+
+namespace {
+int seq_fail_free(sqllm_sequence *s, int rc) {
+    if (s) sqllm_sequence_destroy(s);
+    return rc;
+}
+}  // namespace
+
+extern "C" size_t sqllm_sequence_arena_bytes(const sqllm_seq_item *items, int n_items) {
+    if (!items || n_items <= 0) return 0;
+    size_t off = 0;
+    for (int i = 0; i < n_items; ++i) off += (seq_item_len(items[i]) * 4 + 127) / 128 * 128;
+    return off;
+}
+
+extern "C" int sqllm_sequence_create(const sqllm_seq_item *items, int n_items, const sqllm_seq_options *opt, sqllm_sequence **out) {
+    if (!items || !opt || !out || n_items <= 0) return fail(SQLLM_EINVAL, "sequence: null / empty arguments");
+    if (n_items > SEQ_MAX_ITEMS) return fail(SQLLM_EINVAL, "sequence: at most %d items (got %d)", SEQ_MAX_ITEMS, n_items);
+    const int world = opt->world > 0 ? opt->world : 1, rank = opt->rank;
+    if (world > 64 || rank < 0 || rank >= world) return fail(SQLLM_EINVAL, "sequence: bad world / rank (%d / %d)", world, rank);
+    if (world > 1 && (!opt->arena || !opt->peer_base)) return fail(SQLLM_EINVAL, "sequence: several GPUs need a peer-visible arena and peer_base");
+    const int bits = items[0].a.bits, mode = opt->lut_mode == SQLLM_LUT_FP16_PAIR ? 1 : 0;
+    int kmax = 0;
+    for (int i = 0; i < n_items; ++i) {
+        const sqllm_seq_item &it = items[i];
+        sqllm_lutgemv_args a = it.a;
+        a.batch = 1;
+        a.vec = reinterpret_cast<const float *>(16);  // (vec / mul are not used by a sequence; check_common wants them non-null)
+        a.mul = reinterpret_cast<float *>(16);
+        const int rc = check_common(&a);
+        if (rc) return rc;
+        if (a.bits != bits) return fail(SQLLM_EINVAL, "sequence: item %d has bits=%d, item 0 has %d (one sequence, one width)", i, a.bits, bits);
+        if (a.out_features < STRIP) return fail(SQLLM_EINVAL, "sequence: item %d: out_features=%d < %d", i, a.out_features, STRIP);
+        if (a.out_features > MAX_N_FUSED) return fail(SQLLM_EINVAL, "sequence: item %d: out_features=%d exceeds %d", i, a.out_features, MAX_N_FUSED);
+        if (a.full_rows && a.topX > MAX_TOPX_FUSED) return fail(SQLLM_EINVAL, "sequence: topX <= %d", MAX_TOPX_FUSED);
+        const int members = it.members > 0 ? it.members : 1;
+        if (a.out_features % members || (a.out_features / members) % 4) return fail(SQLLM_EINVAL, "sequence: item %d: %d columns are not %d members of a multiple of 4", i, a.out_features, members);
+        if (world == 1 && seq_item_len(it) != (size_t)a.out_features) return fail(SQLLM_EINVAL, "sequence: item %d: members * out_features_full must equal out_features on one GPU", i);
+        if (world > 1 && seq_item_len(it) < (size_t)world * a.out_features) return fail(SQLLM_EINVAL, "sequence: item %d: full length %zu < world * shard columns", i, seq_item_len(it));
+        if (world > 1 && it.y) return fail(SQLLM_EINVAL, "sequence: item %d: plain y copies exist on one GPU only (use exports)", i);
+        if (seq_item_len(it) % 4) return fail(SQLLM_EINVAL, "sequence: item %d: output length must be a multiple of 4", i);
+        if (it.x_from >= i || it.x_from < -1) return fail(SQLLM_EINVAL, "sequence: item %d: x_from=%d must name an earlier item (or -1)", i, it.x_from);
+        if (it.x_from < 0) {
+            if (!it.x_ext || (reinterpret_cast<uintptr_t>(it.x_ext) & 15)) return fail(SQLLM_EINVAL, "sequence: item %d: x_ext must be a 16-byte aligned fp16 vector", i);
+        } else {
+            if (it.x_offset < 0 || it.x_offset % 4 || (size_t)it.x_offset + a.in_features > seq_item_len(items[it.x_from]))
+                return fail(SQLLM_EINVAL, "sequence: item %d reads [%d, %d) of item %d's %zu outputs", i, it.x_offset, it.x_offset + a.in_features, it.x_from, seq_item_len(items[it.x_from]));
+        }
+        if ((reinterpret_cast<uintptr_t>(it.y) & 1) || (reinterpret_cast<uintptr_t>(it.bias) & 3)) return fail(SQLLM_EINVAL, "sequence: item %d: misaligned y / bias", i);
+        kmax = std::max(kmax, a.in_features);
+    }
+    for (int e = 0; e < opt->n_export; ++e) {
+        if (!opt->export_items || !opt->export_dst) return fail(SQLLM_EINVAL, "sequence: export arrays missing");
+        const int it = opt->export_items[e];
+        if (it < 0 || it >= n_items || !opt->export_dst[e] || (reinterpret_cast<uintptr_t>(opt->export_dst[e]) & 7))
+            return fail(SQLLM_EINVAL, "sequence: export %d: bad item %d or destination (8-byte aligned fp16 vector)", e, it);
+    }
+    // device attributes, shared-memory window, kernel attribute (make_plan2 does the one-time probe)
+    Plan2 probe;
+    K2Info ki2;
+    int rc = make_plan2(bits, items[0].a.in_features, items[0].a.out_features, 0, mode ? 2 : 1, true, probe, ki2);
+    if (rc) return rc;
+    const KSeqInfo ki = kseq_lookup(bits, mode, world > 1);
+    int dev = 0, sm = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_state_mu);
+        sm = g_dev[dev].sm;
+    }
+    if (cudaFuncSetAttribute(ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        return fail(SQLLM_ECUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    // shared memory, exactly as lutgemv_seq_kernel carves it: [fixed][x][strip sums][ring stages ...][tables][... ring stages]
+    const unsigned raw = probe.smem_raw, base = (raw + 127u) & ~127u;
+    const int xbytes = (kmax * 2 + 127) & ~127;
+    const unsigned lo_base = base + v2::OFF_X + (unsigned)xbytes + (unsigned)ki.ntb * STRIP * 4;
+    const unsigned tab0 = (lo_base + (unsigned)ki.tab - 1u) & ~((unsigned)ki.tab - 1u);
+    const long long limit = (long long)raw + 227 * 1024;
+    const long long hi_room = limit - ((long long)tab0 + (long long)ki.ntb * ki.tab);
+    if (hi_room < 0) return fail(SQLLM_EINVAL, "sequence: in_features=%d does not fit the shared-memory carve-up of this table mode", kmax);
+    const int lo_cap = (int)((tab0 - lo_base) / (unsigned)ki.stage), hi_cap = (int)(hi_room / ki.stage);
+    int nst = std::min(v2::MAXD, lo_cap + hi_cap);
+    if (nst < 2) return fail(SQLLM_EINVAL, "sequence: in_features=%d leaves no room for a weight ring in shared memory", kmax);
+    const int n_lo = std::min(nst, lo_cap);
+    const int smem = (int)((long long)tab0 + (long long)ki.ntb * ki.tab + (long long)(nst - n_lo) * ki.stage - raw);
+
+    sqllm_sequence *s = new sqllm_sequence();
+    s->dev = dev; s->n = n_items; s->bits = bits; s->mode = mode; s->world = world; s->rank = rank; s->grid = sm; s->smem = smem; s->fn = ki.fn;
+    {
+        const char *e = getenv("SQLLM_SEQ_COOP");
+        s->coop = (e && e[0] == '0') ? 0 : 1;
+    }
+    // workspace: [0,4) token counter, [64,68) error word, then per parity {flags [64 + MAX_STRIPS] ints, accumulator [MAX_N_FUSED] floats},
+    // then the mailboxes (shared by all items: their words carry the item in the tag)
+    const size_t cnt_bytes = (size_t)(64 + MAX_STRIPS) * 4, acc_bytes = (size_t)MAX_N_FUSED * 4;
+    const size_t par_off = 256, par_bytes = (cnt_bytes + acc_bytes + 255) / 256 * 256;
+    const size_t hbox_off = par_off + 2 * par_bytes, cbox_off = hbox_off + (size_t)MAX_GRID_V2 * 64 * 8, ws_bytes = cbox_off + (size_t)MAX_N_FUSED * 8;
+    if (cudaMalloc(&s->d_ws, ws_bytes) != cudaSuccess || cudaMemset(s->d_ws, 0, ws_bytes) != cudaSuccess)
+        return seq_fail_free(s, fail(SQLLM_ECUDA, "sequence: workspace allocation failed"));
+    unsigned char *ws = static_cast<unsigned char *>(s->d_ws);
+    const size_t arena_need = sqllm_sequence_arena_bytes(items, n_items);
+    if (opt->arena) {
+        if (opt->arena_bytes < arena_need || (reinterpret_cast<uintptr_t>(opt->arena) & 127))
+            return seq_fail_free(s, fail(SQLLM_EINVAL, "sequence: arena of %zu bytes (128-byte aligned) needed, got %zu", arena_need, opt->arena_bytes));
+        s->d_arena = opt->arena;
+    } else {
+        if (cudaMalloc(&s->d_arena, arena_need) != cudaSuccess || cudaMemset(s->d_arena, 0, arena_need) != cudaSuccess)
+            return seq_fail_free(s, fail(SQLLM_ECUDA, "sequence: arena allocation failed"));
+        s->own_arena = true;
+    }
+    std::vector<seq::SeqDesc> descs(n_items);
+    std::vector<size_t> yoff(n_items);
+    size_t off = 0;
+    for (int i = 0; i < n_items; ++i) {
+        yoff[i] = off;
+        off += (seq_item_len(items[i]) * 4 + 127) / 128 * 128;
+    }
+    for (int i = 0; i < n_items; ++i) {
+        const sqllm_seq_item &it = items[i];
+        const sqllm_lutgemv_args &a = it.a;
+        seq::SeqDesc &d = descs[i];
+        memset(&d, 0, sizeof(d));
+        v2::P2 &p = d.p;
+        const bool hyb = a.full_rows && a.topX > 0;
+        const int K = a.in_features, N = a.out_features;
+        p.qw = reinterpret_cast<const uint32_t *>(a.qweight);
+        p.lut = a.lookup_table;
+        p.rows = a.rows; p.cols = a.cols; p.vals = a.vals;
+        p.full_rows = hyb ? a.full_rows : nullptr;
+        p.fri = hyb ? a.full_row_indices : nullptr;
+        p.topX = hyb ? a.topX : 0;
+        p.K = K; p.N = N;
+        p.R = bits == 4 ? K / 8 : K / 32;
+        p.strips = (N + STRIP - 1) / STRIP;
+        const long long T = (long long)p.strips * p.R;
+        if (T > 0x3fffffff) return seq_fail_free(s, fail(SQLLM_EINVAL, "sequence: item %d too large", i));
+        p.T = (int)T;
+        int chunk = (int)(2 * ((T + 2LL * sm - 1) / (2LL * sm)));
+        if (chunk < 2) chunk = 2;
+        p.chunk = chunk;
+        const int G = (int)((T + chunk - 1) / chunk);
+        if (G > MAX_GRID_V2) return seq_fail_free(s, fail(SQLLM_EINVAL, "sequence: grid of %d CTAs exceeds the mailbox area", G));
+        p.nstage = nst; p.smem_raw = raw;
+        p.csr_rpc = (N + G - 1) / G;
+        if (a.rows && p.csr_rpc > v2::SP_ROWS) return seq_fail_free(s, fail(SQLLM_EINVAL, "sequence: item %d: %d outlier rows per CTA exceed %d", i, p.csr_rpc, v2::SP_ROWS));
+        p.hc = p.hrows = 0;
+        if (hyb) {
+            p.hrows = (K + G - 1) / G;
+            p.hc = (K + p.hrows - 1) / p.hrows;
+        }
+        p.csr_al16 = (a.rows && ((reinterpret_cast<uintptr_t>(a.cols) | reinterpret_cast<uintptr_t>(a.vals)) & 15) == 0) ? 1 : 0;
+        p.y_is_half = 1;
+        p.bias = it.bias;
+        p.out = it.y;
+        p.x = it.x_from < 0 ? it.x_ext : nullptr;
+        unsigned char *par = ws + par_off + (size_t)(i & 1) * par_bytes;
+        p.ws_cnt = reinterpret_cast<int *>(par);
+        p.ws_acc = reinterpret_cast<float *>(par + cnt_bytes);
+        p.ws_hbox = reinterpret_cast<unsigned long long *>(ws + hbox_off);
+        p.ws_cbox = reinterpret_cast<unsigned long long *>(ws + cbox_off);
+        p.xw_world = world > 1 ? world : 0; p.xw_rank = rank;
+        p.xw_members = it.members > 0 ? it.members : 1;
+        p.xw_nfull = it.out_features_full > 0 ? it.out_features_full : N / p.xw_members;
+        p.trace = opt->trace ? reinterpret_cast<unsigned long long *>(opt->trace) + (size_t)i * 1024 * 32 : nullptr;
+        d.x_tag = it.x_from < 0 ? nullptr : reinterpret_cast<const uint32_t *>(static_cast<unsigned char *>(s->d_arena) + yoff[it.x_from]) + it.x_offset;
+        d.y_off = yoff[i];
+        const int rows_per_unit = bits == 4 ? 1 : 3, qrows = K / 32 * bits;
+        rc = get_tensor_map(a.qweight, qrows, N, qrows < v2::SU2 * rows_per_unit ? 2 * rows_per_unit : v2::SU2 * rows_per_unit, d.tm_big);
+        if (!rc) rc = get_tensor_map(a.qweight, qrows, N, 2 * rows_per_unit, d.tm_small);
+        if (rc) return seq_fail_free(s, rc);
+    }
+    std::vector<seq::SeqExport> ex(std::max(1, opt->n_export));
+    for (int e = 0; e < opt->n_export; ++e) {
+        const int it = opt->export_items[e];
+        ex[e].src = reinterpret_cast<const uint32_t *>(static_cast<unsigned char *>(s->d_arena) + yoff[it]);
+        ex[e].dst = opt->export_dst[e];
+        ex[e].n = (int)seq_item_len(items[it]);
+    }
+    if (cudaMalloc(&s->d_descs, descs.size() * sizeof(seq::SeqDesc)) != cudaSuccess ||
+        cudaMemcpy(s->d_descs, descs.data(), descs.size() * sizeof(seq::SeqDesc), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMalloc(&s->d_exports, ex.size() * sizeof(seq::SeqExport)) != cudaSuccess ||
+        cudaMemcpy(s->d_exports, ex.data(), ex.size() * sizeof(seq::SeqExport), cudaMemcpyHostToDevice) != cudaSuccess)
+        return seq_fail_free(s, fail(SQLLM_ECUDA, "sequence: descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+    seq::SeqCfg &c = s->cfg;
+    memset(&c, 0, sizeof(c));
+    c.descs = static_cast<const seq::SeqDesc *>(s->d_descs);
+    c.ngemv = n_items;
+    c.epoch = reinterpret_cast<const unsigned *>(ws);
+    c.err = reinterpret_cast<int *>(ws + 64);
+    c.smem_raw = raw; c.xbytes = xbytes; c.nstage = nst;
+    c.world = world; c.rank = rank;
+    c.peer_base = reinterpret_cast<const unsigned long long *>(opt->peer_base);
+    c.arena_base = reinterpret_cast<unsigned long long>(s->d_arena);
+    c.exports = static_cast<const seq::SeqExport *>(s->d_exports);
+    c.nexport = opt->n_export;
+    *out = s;
+    return SQLLM_OK;
+}
+
+extern "C" int sqllm_sequence_run(sqllm_sequence *s, void *stream) {
+    if (!s) return fail(SQLLM_EINVAL, "sequence: null handle");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    seq::seq_bump_epoch<<<1, 1, 0, st>>>(reinterpret_cast<unsigned *>(s->d_ws));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(s->grid);
+    cfg.blockDim = dim3(v2::THREADS2);
+    cfg.dynamicSmemBytes = s->smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // every CTA waits on every other one: they must all be resident
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = s->coop ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, s->fn, s->cfg);
+    if (e != cudaSuccess) return fail(SQLLM_ECUDA, "sequence launch failed: %s", cudaGetErrorString(e));
+    return SQLLM_OK;
+}
+
+extern "C" int sqllm_sequence_error(sqllm_sequence *s, void *stream) {
+    if (!s) return fail(SQLLM_EINVAL, "sequence: null handle");
+    int h = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemcpyAsync(&h, static_cast<unsigned char *>(s->d_ws) + 64, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+        return fail(SQLLM_ECUDA, "sequence: reading the error word failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return h != 0;
+}
+
+extern "C" void sqllm_sequence_destroy(sqllm_sequence *s) {
+    if (!s) return;
+    cudaFree(s->d_descs);
+    cudaFree(s->d_exports);
+    cudaFree(s->d_ws);
+    if (s->own_arena) cudaFree(s->d_arena);
+    delete s;
+}
+
+namespace {
 
 // ---- batched symbols: tile kernel + outlier kernels (lutgemm_batched.cuh) ----------------------------------------------
 bool g_batched_attr[64] = {};

@@ -147,20 +147,22 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long box_word(float v) { return (1ull << 32) | (unsigned long long)__float_as_uint(v); }
+// `tag` is what makes a word valid: 1 for the one-GEMV kernel (the owner writes the word back to zero), a value unique to the (token, GEMV)
+// for the sequence kernel (lutgemv_seq.cuh), where words are never reset (keep = true): a stale word simply carries an older tag.
+__device__ __forceinline__ unsigned long long box_word(float v, uint32_t tag = 1u) { return ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v); }
 // value of a mailbox word read speculatively as `w`; spins (bounded: 2 s, then the workspace error word) until it is valid; clears it
-__device__ __forceinline__ float box_take(unsigned long long w, unsigned long long *ptr, int *err) {
-    if (!(w >> 32)) {
+__device__ __forceinline__ float box_take(unsigned long long w, unsigned long long *ptr, int *err, const uint32_t tag = 1u, const bool keep = false) {
+    if ((uint32_t)(w >> 32) != tag) {
         unsigned long long t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         do {
             w = ld_relaxed_u64(ptr);
-            if (w >> 32) break;
+            if ((uint32_t)(w >> 32) == tag) break;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (t1 - t0 > 2000000000ull) { *reinterpret_cast<volatile int *>(err) = 1; break; }
         } while (true);
     }
-    st_relaxed_u64(ptr, 0ull);
+    if (!keep) st_relaxed_u64(ptr, 0ull);
     return __uint_as_float((uint32_t)w);
 }
 
@@ -372,7 +374,7 @@ __device__ __forceinline__ float xs_load(const uint32_t xs_u32, const int k) {
 }
 
 template <bool XH, bool FUSED>
-__device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const uint32_t base, const int spw, const int lane, float *acc_out) {
+__device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const uint32_t base, const int spw, const int lane, float *acc_out, const uint32_t boxtag = 1u) {
     const int N = p.N;
     const uint32_t xs_u32 = base + OFF_X;
     const uint32_t stage_u32 = base + OFF_CSR + spw * SP_BYTES;       // this warp's chunk buffer b: cols at +b*SP_CH*8, vals SP_CH*4 further
@@ -601,7 +603,7 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
         // every row of this warp's share gets its word, outlier-free rows included (the owner of the strip waits for all 64 of them)
         __syncwarp();
         if (smem_sums) {
-            for (int i = lane; i < nr; i += 32) st_relaxed_u64(p.ws_cbox + r + i, box_word(srowacc[r - ca + i]));
+            for (int i = lane; i < nr; i += 32) st_relaxed_u64(p.ws_cbox + r + i, box_word(srowacc[r - ca + i], boxtag));
         } else if (nr > 0) {
             __threadfence();  // the red.adds on the value halves come first
             for (int i = lane; i < nr; i += 32) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t *>(p.ws_cbox + r + i) + 1), "r"(1u) : "memory");

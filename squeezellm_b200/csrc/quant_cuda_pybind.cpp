@@ -256,6 +256,80 @@ void lutgemv_fused_exchange(torch::Tensor x, torch::Tensor qweight, torch::Tenso
     check_status(rc, "quant_cuda.lutgemv_fused_exchange");
 }
 
+
+// ---- sequences (include/sqllm_b200.h, sqllm_sequence_*): one persistent launch for a list of dependent fused matvecs -----------
+// items: list of tuples (qweight, lookup_table, bits, bias|None, rows|None, cols|None, vals|None, full_rows|None, full_row_indices|None,
+//                        x_from, x_offset, x_ext|None, members, out_features_full)
+// exports: list of (item index, fp16 destination tensor of the item's full output length).  The caller keeps every tensor alive for the
+// life of the handle (squeezellm_b200.runtime.DecodeSequence does).  peer_base / arena: several GPUs only (0 / None otherwise).
+int64_t sequence_create(py::list items, py::list exports, const std::string &lut_mode, int world, int rank,
+                        c10::optional<torch::Tensor> arena, int64_t peer_base) {
+    TORCH_CHECK(lut_mode == "exact" || lut_mode == "fp16", "lut mode must be 'exact' or 'fp16'");
+    const int n = (int)items.size();
+    TORCH_CHECK(n > 0, "sequence_create: no items");
+    std::vector<sqllm_seq_item> its(n);
+    c10::optional<torch::Tensor> first;
+    for (int i = 0; i < n; ++i) {
+        py::tuple t = items[i].cast<py::tuple>();
+        TORCH_CHECK(t.size() == 14, "sequence item ", i, ": expected a 14-tuple");
+        auto opt = [&](int k) -> c10::optional<torch::Tensor> {
+            if (t[k].is_none()) return c10::nullopt;
+            return t[k].cast<torch::Tensor>();
+        };
+        torch::Tensor qweight = t[0].cast<torch::Tensor>(), lut = t[1].cast<torch::Tensor>();
+        const int bits = t[2].cast<int>();
+        sqllm_seq_item &it = its[i];
+        memset(&it, 0, sizeof(it));
+        it.x_from = t[9].cast<int>();
+        it.x_offset = t[10].cast<int>();
+        it.members = t[12].cast<int>();
+        it.out_features_full = t[13].cast<int>();
+        TORCH_CHECK(qweight.is_cuda() && qweight.dim() == 2 && (bits == 3 || bits == 4), "sequence item ", i, ": qweight must be a packed CUDA matrix");
+        const int K = (int)(qweight.size(0) / bits * 32);
+        torch::Tensor xs;  // what the shared checks look at (device, dtype, numel): the external input, or a stand-in of the right length
+        if (it.x_from < 0) {
+            TORCH_CHECK(!t[11].is_none(), "sequence item ", i, ": x_from = -1 needs x_ext");
+            xs = t[11].cast<torch::Tensor>();
+            TORCH_CHECK(xs.scalar_type() == torch::kFloat16, "sequence item ", i, ": x_ext must be fp16");
+        } else {
+            xs = torch::empty({(int64_t)K}, torch::TensorOptions().dtype(torch::kFloat16).device(qweight.device()));
+        }
+        const float *bias_p = nullptr;
+        fill_fused_args(it.a, bias_p, xs, qweight, lut, bits, opt(3), opt(4), opt(5), opt(6), opt(7), opt(8));
+        if (it.x_from < 0) it.x_ext = xs.data_ptr();
+        it.bias = bias_p;
+        if (!first.has_value()) first = qweight;
+    }
+    const at::cuda::OptionalCUDAGuard guard(device_of(*first));
+    const int ne = (int)exports.size();
+    std::vector<int> ex_items(std::max(1, ne));
+    std::vector<void *> ex_dst(std::max(1, ne));
+    for (int e = 0; e < ne; ++e) {
+        py::tuple t = exports[e].cast<py::tuple>();
+        ex_items[e] = t[0].cast<int>();
+        torch::Tensor d = t[1].cast<torch::Tensor>();
+        TORCH_CHECK(d.is_cuda() && d.is_contiguous() && d.scalar_type() == torch::kFloat16, "export ", e, ": destination must be a contiguous fp16 CUDA tensor");
+        TORCH_CHECK(ex_items[e] >= 0 && ex_items[e] < n, "export ", e, ": bad item index");
+        const sqllm_seq_item &it = its[ex_items[e]];
+        const int64_t len = (int64_t)(it.members > 0 ? it.members : 1) * (it.out_features_full > 0 ? it.out_features_full : it.a.out_features / std::max(1, it.members));
+        TORCH_CHECK(d.numel() == len, "export ", e, ": destination has ", d.numel(), " elements, the item's output has ", len);
+        ex_dst[e] = d.data_ptr();
+    }
+    sqllm_seq_options o;
+    memset(&o, 0, sizeof(o));
+    o.lut_mode = lut_mode == "fp16" ? SQLLM_LUT_FP16_PAIR : SQLLM_LUT_EXACT;
+    o.world = world; o.rank = rank;
+    if (arena.has_value() && arena->defined()) {
+        o.arena = arena->data_ptr();
+        o.arena_bytes = (size_t)arena->numel() * arena->element_size();
+    }
+    o.peer_base = reinterpret_cast<const uint64_t *>(peer_base);
+    o.n_export = ne; o.export_items = ex_items.data(); o.export_dst = ex_dst.data();
+    sqllm_sequence *h = nullptr;
+    check_status(sqllm_sequence_create(its.data(), n, &o, &h), "quant_cuda.sequence_create");
+    return reinterpret_cast<int64_t>(h);
+}
+
 torch::Tensor unpack_indices(torch::Tensor qweight, int bits) {
     const at::cuda::OptionalCUDAGuard guard(device_of(qweight));
     need(qweight, "qweight", torch::kInt32, qweight);
@@ -295,6 +369,22 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("vals"), py::arg("full_rows"), py::arg("full_row_indices"), py::arg("peer_base"), py::arg("out_offset"),
           py::arg("flag_offset"), py::arg("state_offset"), py::arg("error_offset"), py::arg("world"), py::arg("rank"), py::arg("members"),
           py::arg("out_features_full"));
+    m.def("sequence_create", &sequence_create, "one persistent launch for a list of dependent fused matvecs (see squeezellm_b200.runtime.DecodeSequence)",
+          py::arg("items"), py::arg("exports"), py::arg("lut_mode") = "exact", py::arg("world") = 1, py::arg("rank") = 0,
+          py::arg("arena") = py::none(), py::arg("peer_base") = 0);
+    m.def("sequence_arena_bytes", [](py::list lens) {
+              size_t off = 0;
+              for (auto l : lens) off += ((size_t)l.cast<int64_t>() * 4 + 127) / 128 * 128;
+              return (int64_t)off;
+          }, "arena bytes for items with these full output lengths");
+    m.def("sequence_run", [](int64_t h) { check_status(sqllm_sequence_run(reinterpret_cast<sqllm_sequence *>(h), cur_stream()), "quant_cuda.sequence_run"); },
+          "run the sequence on the current stream (capturable)");
+    m.def("sequence_error", [](int64_t h) {
+              const int rc = sqllm_sequence_error(reinterpret_cast<sqllm_sequence *>(h), cur_stream());
+              TORCH_CHECK(rc >= 0, "sequence_error: ", sqllm_last_error());
+              return rc == 1;
+          }, "True if a bounded in-kernel wait of the sequence ever timed out (synchronises the current stream)");
+    m.def("sequence_destroy", [](int64_t h) { sqllm_sequence_destroy(reinterpret_cast<sqllm_sequence *>(h)); });
     m.def("unpack_indices", &unpack_indices, "GPU unpack of the packed indices -> uint8 [in, out] (test hook)");
     m.def("abi_version", []() { return sqllm_abi_version(); });
     m.def("set_deterministic", [](bool on) { sqllm_set_deterministic(on ? 1 : 0); },

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     lib = load_lib()
-    assert lib.sqllm_abi_version() == 3
+    assert lib.sqllm_abi_version() == 4
     assert isinstance(lib.sqllm_last_error(), bytes)
 
 
@@ -68,7 +68,7 @@ def test_quant_cuda_module_has_the_reference_names():
     for s in REFERENCE_SYMBOLS:
         assert callable(getattr(quant_cuda, s))
     assert not any("balanced" in n for n in dir(quant_cuda))  # absent in the reference build too
-    assert quant_cuda.abi_version() == 3
+    assert quant_cuda.abi_version() == 4
 
 
 def test_quant_cuda_rejects_cpu_tensors_loudly():

@@ -1886,6 +1886,7 @@ extern "C" int sqllm_sequence_create(const sqllm_seq_item *items, int n_items, c
     if (hi_room < 0) return fail(SQLLM_EINVAL, "sequence: in_features=%d does not fit the shared-memory carve-up of this table mode", kmax);
     const int lo_cap = (int)((tab0 - lo_base) / (unsigned)ki.stage), hi_cap = (int)(hi_room / ki.stage);
     int nst = std::min(v2::MAXD, lo_cap + hi_cap);
+    if (const char *e = getenv("SQLLM_SEQ_STAGES")) nst = std::max(2, std::min(nst, atoi(e)));  // experiments: a shallower weight ring
     if (nst < 2) return fail(SQLLM_EINVAL, "sequence: in_features=%d leaves no room for a weight ring in shared memory", kmax);
     const int n_lo = std::min(nst, lo_cap);
     const int smem = (int)((long long)tab0 + (long long)ki.ntb * ki.tab + (long long)(nst - n_lo) * ki.stage - raw);
@@ -1896,11 +1897,20 @@ extern "C" int sqllm_sequence_create(const sqllm_seq_item *items, int n_items, c
         const char *e = getenv("SQLLM_SEQ_COOP");
         s->coop = (e && e[0] == '0') ? 0 : 1;
     }
-    // workspace: [0,4) token counter, [64,68) error word, then per parity {flags [64 + MAX_STRIPS] ints, accumulator [MAX_N_FUSED] floats},
-    // then the mailboxes (shared by all items: their words carry the item in the tag)
+    // workspace: [0,4) token counter, [64,68) error word, per parity {flags [64 + MAX_STRIPS] ints, accumulator [MAX_N_FUSED] floats} (only
+    // used by CTAs that own more than 8 strips), then EVERY item's own mailboxes: outlier row sums [N], partial strip sums [grid][64],
+    // dense-row parts [topX][MAX_GRID_V2].  Mailboxes are not shared between items: an item may read only a slice of its predecessor's
+    // output, so "x of item g+1 is complete" does not mean that every strip owner of item g has already taken its words.
     const size_t cnt_bytes = (size_t)(64 + MAX_STRIPS) * 4, acc_bytes = (size_t)MAX_N_FUSED * 4;
     const size_t par_off = 256, par_bytes = (cnt_bytes + acc_bytes + 255) / 256 * 256;
-    const size_t hbox_off = par_off + 2 * par_bytes, cbox_off = hbox_off + (size_t)MAX_GRID_V2 * 64 * 8, ws_bytes = cbox_off + (size_t)MAX_N_FUSED * 8;
+    std::vector<size_t> cbox_off(n_items), hbox_off(n_items), dbox_off(n_items);
+    size_t ws_bytes = par_off + 2 * par_bytes;
+    for (int i = 0; i < n_items; ++i) {
+        const bool hyb = items[i].a.full_rows && items[i].a.topX > 0;
+        cbox_off[i] = ws_bytes; ws_bytes += ((size_t)items[i].a.out_features * 8 + 255) / 256 * 256;
+        hbox_off[i] = ws_bytes; ws_bytes += (size_t)MAX_GRID_V2 * 64 * 8;
+        dbox_off[i] = ws_bytes; ws_bytes += hyb ? (size_t)items[i].a.topX * MAX_GRID_V2 * 8 : 0;
+    }
     if (cudaMalloc(&s->d_ws, ws_bytes) != cudaSuccess || cudaMemset(s->d_ws, 0, ws_bytes) != cudaSuccess)
         return seq_fail_free(s, fail(SQLLM_ECUDA, "sequence: workspace allocation failed"));
     unsigned char *ws = static_cast<unsigned char *>(s->d_ws);
@@ -1962,8 +1972,9 @@ extern "C" int sqllm_sequence_create(const sqllm_seq_item *items, int n_items, c
         unsigned char *par = ws + par_off + (size_t)(i & 1) * par_bytes;
         p.ws_cnt = reinterpret_cast<int *>(par);
         p.ws_acc = reinterpret_cast<float *>(par + cnt_bytes);
-        p.ws_hbox = reinterpret_cast<unsigned long long *>(ws + hbox_off);
-        p.ws_cbox = reinterpret_cast<unsigned long long *>(ws + cbox_off);
+        p.ws_hbox = reinterpret_cast<unsigned long long *>(ws + hbox_off[i]);
+        p.ws_cbox = reinterpret_cast<unsigned long long *>(ws + cbox_off[i]);
+        p.ws_dbox = reinterpret_cast<unsigned long long *>(ws + dbox_off[i]);
         p.xw_world = world > 1 ? world : 0; p.xw_rank = rank;
         p.xw_members = it.members > 0 ? it.members : 1;
         p.xw_nfull = it.out_features_full > 0 ? it.out_features_full : N / p.xw_members;

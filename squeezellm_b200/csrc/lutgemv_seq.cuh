@@ -16,6 +16,14 @@
 //     next GEMV is the whole exchange - no collective, no flag round trip (v2's exchange waited ~10 us per launch on a system-scope flag).
 #pragma once
 
+#ifndef SQLLM_SEQ_POLL_NS
+#define SQLLM_SEQ_POLL_NS 0   // pause between two reads of an x word that is not there yet
+#endif
+
+#ifndef SQLLM_SEQ_PREFETCH
+#define SQLLM_SEQ_PREFETCH 0  // 1: consumer loop fetches the next stage's words before the current stage's gathers (register rotation); measured: no gain (4-bit), spills (3-bit)
+#endif
+
 namespace seq {
 using namespace v2;
 
@@ -72,6 +80,9 @@ __device__ __forceinline__ void poll_tagged(const uint32_t *src, const int n4, c
             const int i = i0 + j * nthr;
             if (i < n4) {
                 while (!tags_ok(w[j], want)) {
+#if SQLLM_SEQ_POLL_NS > 0
+                    __nanosleep(SQLLM_SEQ_POLL_NS);
+#endif
                     w[j] = ld_relaxed_v4<SYS>(src + 4 * (size_t)i);
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                     if (t0 == 0ull) t0 = t1;
@@ -80,6 +91,169 @@ __device__ __forceinline__ void poll_tagged(const uint32_t *src, const int n4, c
                 sink(i, __byte_perm(w[j].x, w[j].y, 0x5410), __byte_perm(w[j].z, w[j].w, 0x5410));
             }
         }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Outlier warps of the sequence kernel.  v2::sparse2 stages the (col, val) chunks in shared memory, forms the products in place and sums
+// rows from there: four or more DEPENDENT shared-memory round trips per chunk, each queueing for hundreds of cycles behind the consumers'
+// gathers (the LSU is what bounds the kernel) - the timeline of a 4096x4096 layer showed the outlier warps finishing 7 us after x arrived
+// for 510 non-zeros per CTA, 2.3 us after the last consumer warp: they, not the weights, set the layer's critical path
+// (profiles/r02_seq_trace_1.txt).  Here nothing but x goes through shared memory:
+//   * LPR lanes share a row (LPR from the average row length), 32 / LPR rows per pass; a lane keeps its <= 8 (col, val) pairs of the
+//     pass in REGISTERS, loaded straight from global memory (L2: prefetched at entry) - everything static, so the first pass is in
+//     registers before x arrives and the loads of pass k+1 are issued before pass k is summed;
+//   * after x: one round of x gathers (the only shared-memory accesses), FMAs, a shuffle tree over the LPR lanes, and ONE 64-bit tagged
+//     store of the row sum into the row's mailbox word (rows without outliers store 0: the strip's owner waits for all its rows);
+//   * the part of a row beyond 8 x LPR elements is summed by the whole warp (skewed rows).
+// Dense rows (topX): as in v2 (the CTA's k-slice, requested before x arrives, red.add + one announcement per strip).
+// ---------------------------------------------------------------------------------------------------------------------------
+template <bool XH>
+__device__ __forceinline__ void sparse3(const P2 &p, const uint32_t base, const int spw, const int lane, const uint32_t boxtag) {
+    const int N = p.N;
+    const uint32_t xs_u32 = base + OFF_X;
+    // ---------------- static: dense-row slice ----------------
+    float hfr[HYB_R2];
+    const bool hyb_on = p.full_rows && spw == 0 && (int)blockIdx.x < p.hc;
+    const bool hyb_multi = hyb_on && p.topX <= 32;
+    int kb = 0, ke = 0, nsl = 1, rs = 0, hj = lane;
+    if (hyb_on) { kb = blockIdx.x * p.hrows; ke = min(p.K, kb + p.hrows); }
+    if (hyb_multi) {
+        nsl = 32 / p.topX;
+        rs = lane / p.topX;
+        hj = lane - rs * p.topX;
+#pragma unroll
+        for (int i = 0; i < HYB_R2; ++i) {
+            const int k = kb + rs + nsl * i;
+            hfr[i] = (rs < nsl && k < ke) ? __ldg(p.full_rows + (size_t)k * p.topX + hj) : 0.f;
+        }
+    }
+    // ---------------- static: this warp's CSR rows [r, rb) of the CTA's [ca, cb) ----------------
+    int r = 0, rb = 0;
+    if (p.rows) {
+        const int ca = min(N, (int)blockIdx.x * p.csr_rpc), cb = min(N, ca + p.csr_rpc);
+        // warp 0 has the dense rows (atomics + a fence before its announcement: ~2-3 us) and then takes no CSR rows: outlier sums are what
+        // the owners of ALL strips wait for, they must not queue behind that fence
+        const int tot = cb - ca, w0 = p.full_rows ? 0 : tot / NSPW, rest = tot - w0;
+        r = spw == 0 ? ca : ca + w0 + (int)((long long)rest * (spw - 1) / (NSPW - 1));
+        rb = spw == 0 ? ca + w0 : ca + w0 + (int)((long long)rest * spw / (NSPW - 1));
+    }
+    const int nr = rb - r;
+    int LPR = 4;
+    if (nr > 0) {
+        const int e_lo = __ldg(p.rows + r), e_hi = __ldg(p.rows + rb);
+        const int avg = (e_hi - e_lo) / nr;
+        LPR = avg > 128 ? 32 : avg > 64 ? 16 : avg > 32 ? 8 : avg > 8 ? 4 : 2;
+    }
+    const int RPP = 32 / LPR, part = lane & (LPR - 1), rslot = lane / LPR;
+    const int npass = (nr + RPP - 1) / RPP;
+    constexpr int T = 8;  // (col, val) pairs per lane and pass
+    auto load_ptrs = [&](int pass, int &a0, int &a1) {
+        const int row = r + pass * RPP + rslot;
+        a0 = a1 = 0;
+        if (pass < npass && row < rb) { a0 = __ldg(p.rows + row); a1 = __ldg(p.rows + row + 1); }
+    };
+    auto load_elems = [&](int a0, int a1, int (&cc)[T], float (&vv)[T]) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int e = a0 + part + t * LPR;
+            const bool ok = e < a1;
+            cc[t] = ok ? __ldg(p.cols + e) : 0;
+            vv[t] = ok ? __ldg(p.vals + e) : 0.f;
+        }
+    };
+    int a0c, a1c, a0n, a1n, a0nn, a1nn;
+    int cc[T], cn[T];
+    float vv[T], vn[T];
+    load_ptrs(0, a0c, a1c);
+    load_ptrs(1, a0n, a1n);
+    load_elems(a0c, a1c, cc, vv);
+
+    named_bar_sync(2, NCT + NSPW * 32);  // x is in shared memory
+
+    // ---------------- dense rows (v2's phase B) ----------------
+    if (hyb_on) {
+        for (int jb = 0; jb < (hyb_multi ? 1 : p.topX); jb += 32) {
+            float a = 0.f;
+            int j;
+            if (hyb_multi) {
+                j = hj;
+#pragma unroll
+                for (int i = 0; i < HYB_R2; ++i) {
+                    const int k = kb + rs + nsl * i;
+                    if (rs < nsl && k < ke) a += hfr[i] * xs_load<XH>(xs_u32, k);
+                }
+                for (int k = kb + rs + nsl * HYB_R2; rs < nsl && k < ke; k += nsl)
+                    a += __ldg(p.full_rows + (size_t)k * p.topX + hj) * xs_load<XH>(xs_u32, k);
+                for (int sl = 1; sl < nsl; ++sl) {
+                    const float v = __shfl_sync(0xffffffffu, a, (hj + sl * p.topX) & 31);
+                    if (rs == 0) a += v;
+                }
+                if (rs != 0) j = p.topX;
+                // dense rows that feed the SAME channel travel as one word (the first of them carries the sum): the owner of that channel's
+                // strip then reads hc words, not hc per row - a checkpoint without dense rows loads as topX rows on channel 0 (llama.py:182)
+                {
+                    const int cme = (rs == 0 && hj < p.topX) ? __ldg(p.fri + hj) : -1 - lane;
+                    bool first = true;
+                    float tot = a;
+                    for (int j2 = 0; j2 < p.topX; ++j2) {
+                        const int c2 = __shfl_sync(0xffffffffu, cme, j2);
+                        const float a2 = __shfl_sync(0xffffffffu, a, j2);
+                        if (c2 == cme && j2 < hj) first = false;
+                        if (c2 == cme && j2 > hj) tot += a2;
+                    }
+                    a = tot;
+                    if (!first) j = p.topX;
+                }
+            } else {
+                j = jb + lane;
+                if (j < p.topX) {
+                    const float *fr = p.full_rows + (size_t)kb * p.topX + j;
+                    for (int k = kb; k < ke; ++k, fr += p.topX) a += __ldg(fr) * xs_load<XH>(xs_u32, k);
+                }
+            }
+            // this CTA's part of dense row j: one tagged word, no fence, no flag (the owner of the channel's strip sums the hc words of row j)
+            if (j < p.topX) st_relaxed_u64(p.ws_dbox + (size_t)j * MAX_GRID_V2 + blockIdx.x, box_word(a, boxtag));
+        }
+    }
+    // ---------------- CSR passes ----------------
+    for (int pass = 0; pass < npass; ++pass) {
+        load_ptrs(pass + 2, a0nn, a1nn);
+        load_elems(a0n, a1n, cn, vn);
+        float s0 = 0.f, s1 = 0.f;
+        {
+            float xv[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) xv[t] = xs_load<XH>(xs_u32, cc[t]);   // (padding slots read x[0] with val 0)
+#pragma unroll
+            for (int t = 0; t < T; t += 2) { s0 = fmaf(vv[t], xv[t], s0); s1 = fmaf(vv[t + 1], xv[t + 1], s1); }
+        }
+        float tot = s0 + s1;
+        for (int d = 1; d < LPR; d <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+        // rows longer than T * LPR: the whole warp sums the remainder, row after row
+        unsigned longm = __ballot_sync(0xffffffffu, part == 0 && a1c - a0c > T * LPR);
+        while (longm) {
+            const int i = __ffs(longm) - 1;
+            longm &= longm - 1;
+            const int b0 = __shfl_sync(0xffffffffu, a0c, i) + T * LPR, b1 = __shfl_sync(0xffffffffu, a1c, i);
+            float a = 0.f, b = 0.f;
+            for (int e = b0 + lane; e < b1; e += 128) {
+                const int c0 = __ldg(p.cols + e), c1 = e + 32 < b1 ? __ldg(p.cols + e + 32) : 0, c2 = e + 64 < b1 ? __ldg(p.cols + e + 64) : 0,
+                          c3 = e + 96 < b1 ? __ldg(p.cols + e + 96) : 0;
+                const float v0 = __ldg(p.vals + e), v1 = e + 32 < b1 ? __ldg(p.vals + e + 32) : 0.f, v2 = e + 64 < b1 ? __ldg(p.vals + e + 64) : 0.f,
+                            v3 = e + 96 < b1 ? __ldg(p.vals + e + 96) : 0.f;
+                a = fmaf(v0, xs_load<XH>(xs_u32, c0), a); b = fmaf(v1, xs_load<XH>(xs_u32, c1), b);
+                a = fmaf(v2, xs_load<XH>(xs_u32, c2), a); b = fmaf(v3, xs_load<XH>(xs_u32, c3), b);
+            }
+            a = warp_sum(a + b);
+            if (lane == i) tot += a;
+        }
+        const int row = r + pass * RPP + rslot;
+        if (part == 0 && row < rb) st_relaxed_u64(p.ws_cbox + row, box_word(tot, boxtag));
+        a0c = a0n; a1c = a1n; a0n = a0nn; a1n = a1nn;
+#pragma unroll
+        for (int t = 0; t < T; ++t) { cc[t] = cn[t]; vv[t] = vn[t]; }
     }
 }
 
@@ -189,8 +363,8 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv_seq_kernel(const SeqCfg c
         // =========================== outlier warps (v2::sparse2, once per GEMV) ===========================
         for (int g = 0; g < ngemv; ++g) {
             const P2 &p = c.descs[g].p;
-            named_bar_sync(5, NSPW * 32);  // the CTA-wide row arrays of the previous GEMV have been published by all four warps
-            sparse2<XH, true>(p, sm, base, warp - WARP_SP, lane, p.ws_acc, (epoch << 10) | (uint32_t)(g + 1));
+            sparse3<XH>(p, base, warp - WARP_SP, lane, (epoch << 10) | (uint32_t)(g + 1));
+            TRACE(10, lane == 0);
             if (g + 1 < ngemv) bar_arrive(6, NCT + NSPW * 32);  // done reading this GEMV's x from shared memory
         }
     } else if (warp >= WARP_BLD) {
@@ -216,12 +390,20 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv_seq_kernel(const SeqCfg c
             int *const flags = p.ws_cnt + 64;
             auto sacc_of = [&](int s) { return sacc0 + 4u * (uint32_t)(((q0 + s) % NTB) * STRIP + bt); };
             auto tfree_wait = [&](int s) { mbar_wait(bar_u32 + 288 + 8 * ((q0 + s) % NTB), (uint32_t)(((q0 + s) / NTB) & 1)); };
-            auto flush = [&](int s) {  // strip sums of segment s: to the strip's owner (mailbox row) or into our own accumulator; sums back to zero
+            // Strip sums of segment s go to the strip's owner: another CTA (mailbox row) if the strip started before our range, else ourselves -
+            // and then they never leave the SM: sown[u][column] for the u-th owned strip (a strip inside one CTA is exactly one segment).
+            // (v2 and the first sequence build sent them through the global accumulator - a RED and, in the finishing pass, a load that has to
+            // wait for it: 1.5 us of L2 round trips on the critical path between the last weight and y, profiles/r02_seq_trace_2.txt.)
+            const uint32_t sown = base + OFF_SROW;  // float [SOWN][64] (the row arrays of v2's outlier warps are not used by the sequence kernel)
+            constexpr int SOWN = (2 * (SP_ROWS + 1) * 4) / (STRIP * 4);
+            const int ofs = r0 != 0 ? 1 : 0;        // segment s is owned strip s - ofs
+            auto flush = [&](int s) {
                 const uint32_t a = sacc_of(s);
                 const float v = lds_f32(a);
                 sts_u32(a, 0u);
                 const int col = (s0 + s) * STRIP + bt;
                 if (s == 0 && r0 != 0) st_relaxed_u64(p.ws_hbox + (size_t)blockIdx.x * STRIP + bt, box_word(v, boxtag));
+                else if (s - ofs < SOWN) sts_u32(sown + 4u * (uint32_t)((s - ofs) * STRIP + bt), __float_as_uint(v));
                 else if (col < N) atomicAdd(acc_out + col, v);
             };
             for (int s = 0; s < nseg; ++s) {
@@ -246,17 +428,39 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv_seq_kernel(const SeqCfg c
                 if (nsegn > 1) lut_prefetch<BITS>(pn, lutbuf + LUTBUF, sn0 + 1, bt);
             }
             // ---- finish the strips this CTA owns (those that start in its range); see lutgemv_v2.cuh for the protocol ----
+            TRACE(12, bt == 0);
+            const long long cb0 = (long long)blockIdx.x * p.chunk, cb1 = min((long long)p.T, cb0 + p.chunk);
+            const int so0 = (int)((cb0 + R - 1) / R), so1 = (int)((cb1 + R - 1) / R), nown = so1 - so0;
+            const bool last_owned = nseg >= 2 || r0 == 0;
+            constexpr int FAST = 4;
+            const int lidx = last_owned && nseg > 0 ? nown - 1 : -1;
+            const int nh = lidx >= 0 ? (int)((((long long)(so1 - 1) + 1) * R - 1) / p.chunk) - (int)blockIdx.x : 0;
+            // Dense rows whose channel lies in a strip we own: listed now (static), summed below.  sdj[i] = dense row, sden[i] = its sum.
+            int *const sdj = reinterpret_cast<int *>(sm + OFF_CSR);
+            const uint32_t sden = base + OFF_CSR + 4 * 128, sdn_a = base + OFF_CSR + 8 * 128;
+            if (p.full_rows) {
+                if (bt == 0) {
+                    int n = 0;
+                    for (int j = 0; j < p.topX; ++j) {
+                        const int cc = __ldg(p.fri + j);
+                        bool first = true;  // (rows on the same channel were combined by the contributors, topX <= 32: see sparse3)
+                        if (p.topX <= 32)
+                            for (int j2 = 0; j2 < j; ++j2) first &= __ldg(p.fri + j2) != cc;
+                        if (first && cc >= 0 && cc < N && cc / STRIP >= so0 && cc / STRIP < so1) sdj[n++] = j;
+                    }
+                    sts_u32(sdn_a, (uint32_t)n);
+                }
+                sts_u32(sden + 4 * bt, 0u);
+                sts_u32(sden + 4 * (bt + NBT), 0u);
+                named_bar_sync(3, NBT);
+            }
+            const int sdn = p.full_rows ? (int)lds_u32(sdn_a) : 0;
             for (int s = max(0, nseg - NTB); s < nseg - 1; ++s) {
                 tfree_wait(s);
                 flush(s);
             }
-            const long long cb0 = (long long)blockIdx.x * p.chunk, cb1 = min((long long)p.T, cb0 + p.chunk);
-            const int so0 = (int)((cb0 + R - 1) / R), so1 = (int)((cb1 + R - 1) / R), nown = so1 - so0;
-            const bool last_owned = nseg >= 2 || r0 == 0;
+            TRACE(13, bt == 0);
             {
-                constexpr int FAST = 4;
-                const int lidx = last_owned && nseg > 0 ? nown - 1 : -1;
-                const int nh = lidx >= 0 ? (int)((((long long)(so1 - 1) + 1) * R - 1) / p.chunk) - (int)blockIdx.x : 0;
                 unsigned long long cw[FAST], hw[3];
 #pragma unroll
                 for (int u = 0; u < FAST; ++u) {
@@ -266,29 +470,47 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv_seq_kernel(const SeqCfg c
 #pragma unroll
                 for (int h = 0; h < 3; ++h)
                     hw[h] = h < nh ? ld_relaxed_u64(p.ws_hbox + ((size_t)blockIdx.x + 1 + h) * STRIP + bt) : box_word(0.f, boxtag);
-                if (p.full_rows) {
-                    for (int i = bt; i < nown; i += NBT) {
-                        const int strip = so0 + i;
-                        bool hch = false;
-                        for (int j = 0; j < p.topX; ++j) {
-                            const int cc = __ldg(p.fri + j);
-                            hch |= (cc >= 0 && cc < N && cc / STRIP == strip);
+                // dense rows: hc tagged words per listed row (one from every contributing CTA), four loads in flight per thread; row sums are
+                // collected in shared memory and added to the column they belong to by the thread that owns that column
+                float last_dense = 0.f;
+                if (sdn > 0) {
+                    const int hc = p.hc;
+                    unsigned long long *const dbox = p.ws_dbox;
+                    for (int j0 = 0; j0 < sdn; j0 += 4) {  // four rows x up to four words per thread in flight (hc <= MAX_GRID_V2 = 4 x NBT)
+                        unsigned long long dw[4][4];
+                        int row[4];
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            row[a] = j0 + a < sdn ? sdj[j0 + a] : -1;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                if (row[a] >= 0 && bt + b * NBT < hc) dw[a][b] = ld_relaxed_u64(dbox + (size_t)row[a] * MAX_GRID_V2 + bt + b * NBT);
                         }
-                        if (hch) {
-                            int seen;
-                            unsigned long long t0 = 0ull, t1;
-                            do {
-                                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + strip) : "memory");
-                                if (seen >= p.hc) break;
-                                __nanosleep(40);
-                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                                if (t0 == 0ull) t0 = t1;
-                                if (t1 - t0 > 2000000000ull) { *reinterpret_cast<volatile int *>(err) = 1; break; }
-                            } while (true);
-                            flags[strip] = 0;
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            if (row[a] < 0) continue;  // (uniform)
+                            float v = 0.f;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                if (bt + b * NBT < hc) v += box_take(dw[a][b], dbox + (size_t)row[a] * MAX_GRID_V2 + bt + b * NBT, err, boxtag, true);
+                            v = warp_sum(v);
+                            if (lane == 0) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sden + 4u * (uint32_t)(j0 + a)), "f"(v) : "memory");
                         }
                     }
                     named_bar_sync(3, NBT);
+                    for (int i = 0; i < sdn; ++i) {
+                        const int cc = __ldg(p.fri + sdj[i]);
+                        if ((cc & (STRIP - 1)) == bt) {
+                            const int u = cc / STRIP - so0;
+                            const float v = lds_f32(sden + 4u * (uint32_t)i);
+                            if (u == lidx) last_dense += v;
+                            else if (u < SOWN) {
+                                const uint32_t a = sown + 4u * (uint32_t)(u * STRIP + bt);
+                                sts_u32(a, __float_as_uint(lds_f32(a) + v));
+                            } else atomicAdd(acc_out + cc, v);
+                        }
+                    }
+                    named_bar_sync(3, NBT);  // (the list and the sums are reused by the next item; an idle CTA has no other barrier before that)
                 }
                 const int w = MULTI ? N / p.xw_members : 0;
                 auto store_y = [&](int col, float yv) {
@@ -305,34 +527,32 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv_seq_kernel(const SeqCfg c
                     }
                     if (p.out) reinterpret_cast<__half *>(p.out)[col] = __float2half_rn(yv);
                 };
-                float av[FAST];
-#pragma unroll
-                for (int u = 0; u < FAST; ++u) {
-                    const int col = (so0 + u) * STRIP + bt;
-                    av[u] = (u < nown && col < N) ? __ldcg(p.ws_acc + col) : 0.f;
-                }
-                float last_others = 0.f;
+                // per owned strip but the last segment's: [our own sums (+ dense rows), from shared memory] + [the column's outlier sum]
+                TRACE(14, bt == 0);
+                float last_others = last_dense;
 #pragma unroll
                 for (int u = 0; u < FAST; ++u) {
                     const int col = (so0 + u) * STRIP + bt;
                     if (u < nown && col < N) {
-                        float yv = av[u];
+                        float yv = 0.f;
+                        if (u != lidx && u < SOWN) yv = lds_f32(sown + 4u * (uint32_t)(u * STRIP + bt));
                         if (p.rows) yv += box_take(cw[u], p.ws_cbox + col, err, boxtag, true);
-                        p.ws_acc[col] = 0.f;
-                        if (u == lidx) last_others = yv;
+                        if (u == lidx) last_others += yv;
                         else store_y(col, yv);
                     }
                 }
-                for (int i = FAST; i < nown; ++i) {
+                for (int i = FAST; i < nown; ++i) {  // (more owned strips than FAST; beyond SOWN the sums went through the global accumulator)
                     const int col = (so0 + i) * STRIP + bt;
                     if (col < N) {
-                        float yv = __ldcg(p.ws_acc + col);
+                        float yv = 0.f;
+                        if (i >= SOWN) { yv = __ldcg(p.ws_acc + col); p.ws_acc[col] = 0.f; }
+                        else if (i != lidx) yv = lds_f32(sown + 4u * (uint32_t)(i * STRIP + bt));
                         if (p.rows) yv += box_take(0ull, p.ws_cbox + col, err, boxtag, true);
-                        p.ws_acc[col] = 0.f;
-                        if (i == lidx) last_others = yv;
+                        if (i == lidx) last_others += yv;
                         else store_y(col, yv);
                     }
                 }
+                TRACE(15, bt == 0);
 #pragma unroll
                 for (int h = 0; h < 3; ++h)
                     if (h < nh) last_others += box_take(hw[h], p.ws_hbox + ((size_t)blockIdx.x + 1 + h) * STRIP + bt, err, boxtag, true);
@@ -409,6 +629,31 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv_seq_kernel(const SeqCfg c
                 const int mine = 2 * warp < seglen ? (seglen - 2 * warp + SU2 - 1) / SU2 : 0;
                 mbar_wait(bar_u32 + 256 + 8 * b, (uint32_t)((q / NTB) & 1));
                 TRACE(16 + (seg < 7 ? seg : 7), tid == 0);
+#if SQLLM_SEQ_PREFETCH
+                // The words (and x slice) of stage k+1 are requested BEFORE the gathers of stage k are issued: one of the two serialized
+                // shared-memory round trips per position (word fetch, then gathers - each queues behind the other warps' gathers in the LSU)
+                // disappears from a warp's critical path.  One copy of the math, the look-ahead lives in a second register set that is
+                // moved over at the end of the trip (8 / 12 MOVs per ~140 instructions); the loop is kept rolled (i-cache: see v2).
+                {
+                    Fetch<BITS, XH> F, Fn;
+                    mbar_wait(bar_u32 + 8 * slot, par);
+                    if (0 < mine) fetch2<BITS, XH>(F, stage_of(slot), xaddr);
+#pragma unroll 1
+                    for (int k = 0; k < nstg; ++k) {
+                        const int cur = slot;
+                        advance();
+                        if (k + 1 < nstg) {
+                            mbar_wait(bar_u32 + 8 * slot, par);
+                            if (k + 1 < mine) fetch2<BITS, XH>(Fn, stage_of(slot), xaddr + XBS);
+                        }
+                        if (k < mine) math2<BITS, MODE, XH>(F, jsel, l, segc, xaddr, A);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_u32 + 128 + 8 * cur);
+                        F = Fn;
+                        xaddr += XBS;
+                    }
+                }
+#else
                 for (int k = 0; k < nstg; ++k) {
                     mbar_wait(bar_u32 + 8 * slot, par);
                     if (k < mine) {
@@ -421,6 +666,7 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv_seq_kernel(const SeqCfg c
                     advance();
                     xaddr += XBS;
                 }
+#endif
                 {
                     float s[4];
 #pragma unroll

@@ -77,6 +77,7 @@ struct P2 {
     float *ws_acc;       // fused: [N] fp32 accumulator, zero between launches
     unsigned long long *ws_hbox;  // fused, SQLLM_BOX: [grid][64] partial strip sums of a CTA's first segment when the strip starts in an earlier CTA
     unsigned long long *ws_cbox;  // fused, SQLLM_BOX: [N] outlier (CSR) row sums; both {float value, u32 valid}, all zero between launches
+    unsigned long long *ws_dbox;  // sequence kernel: [topX][MAX_GRID_V2] dense-row partial sums, one tagged word per (dense row, contributing CTA)
     int *ws_cnt;         // fused: [16] error flag (a bounded wait gave up; sqllm_workspace_error), [64 + s] arrivals on strip s (zero between launches)
     int strips;          // output strips of 64 columns
     int nown_ctas;       // exchange: CTAs that own at least one strip (each announces itself once on every rank)

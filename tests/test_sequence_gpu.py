@@ -26,6 +26,9 @@ def _chain(bits, dims, sparsity, topX, seed):
         L = orc.make_layer(bits, K, N, sparsity=sparsity, topX=topX, seed=seed + 17 * i, nonzero_full_rows=True)
         if topX and sparsity == 0:
             L["full_rows"] = L["full_row_indices"] = None
+        elif topX >= 3 and i % 2 == 0:  # dense rows that feed the same output channel (their parts travel combined), one of them channel 0
+            L["full_row_indices"][1] = L["full_row_indices"][0]
+            L["full_row_indices"][2] = 0
         # keep activations O(1) through the chain
         L["lookup_table"] = (L["lookup_table"] * (50.0 / np.sqrt(K))).astype(np.float32)  # centroids ~ N(0, 1/K): |y| ~ |x|
         layers.append(L)

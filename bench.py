@@ -377,9 +377,10 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how column shards are reassembled - p2p: stores into every rank's symmetric arena from inside the GEMV "
                          "kernel (falls back to nccl if symmetric memory is unavailable or the self-check fails); nccl: one all-reduce per launch")
-    ap.add_argument("--launch", default="seq", choices=["seq", "graph"],
-                    help="seq (default, single GPU): the whole token as ONE persistent kernel launch (runtime.DecodeSequence, csrc/lutgemv_seq.cuh); "
-                         "graph: one launch per (stacked) matvec, chained with PDL inside a CUDA graph (round 1 / early round 2)")
+    ap.add_argument("--launch", default="auto", choices=["auto", "seq", "graph"],
+                    help="graph: one launch per (stacked) matvec, chained with PDL inside a CUDA graph; seq: the whole token as ONE persistent "
+                         "kernel launch (runtime.DecodeSequence, csrc/lutgemv_seq.cuh; on several GPUs its input poll is the exchange); "
+                         "auto (default): what measured faster - graph on one GPU (500 vs 473 tokens/s), seq on several (509 vs 371 at N=2)")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinearLUT (no q/k/v and gate/up sibling stacking)")
     ap.add_argument("--lut", default="both", choices=["both", "exact", "fp16"],
                     help="codebook precision: exact = fp32 as stored (headline), fp16 = pair tables; both = headline exact + a lut_fp16 object")
@@ -432,12 +433,20 @@ def main():
                 nlaunch -= len(names) - 1
         torch.cuda.empty_cache()
     exchange_used, peer_used = "none", None
+    use_seq = args.launch == "seq" or (args.launch == "auto" and world > 1)
+    seq_peer = None
+    if world > 1 and use_seq:
+        from squeezellm_b200.sharding import PeerArena
+        seq_peer = PeerArena(rank, world, dev)
     if world > 1:
         import torch.distributed as dist
         step_nccl, run_layer_nccl = make_step(layers, world)
         run_layer = run_layer_nccl
         step, exchange_used = step_nccl, "nccl all-reduce per launch"
-        if args.exchange == "p2p":
+        if use_seq:
+            exchange_used = ("sequence kernel: strip owners store tagged result words into every rank's arena over NVLink; the next matvec's "
+                             "input poll is the exchange (no collective)")
+        elif args.exchange == "p2p":
             why, ok, step_p2p = None, 0.0, None
             try:
                 from squeezellm_b200.sharding import PeerExchange
@@ -462,8 +471,7 @@ def main():
                 print(f"[bench] rank {rank}: p2p exchange not used ({why or 'another rank declined'}); falling back to NCCL", file=sys.stderr)
     else:
         step, run_layer = make_step(layers, world)
-    use_seq = args.launch == "seq" and world == 1
-    x0 = torch.randn(cfg["hidden"], device=dev).half()
+    x0 = torch.randn(cfg["hidden"], device=dev, generator=torch.Generator(device=dev).manual_seed(99)).half()  # same on every rank
 
     def barrier():
         if world > 1:
@@ -484,7 +492,7 @@ def main():
         seq = None
         try:
             if use_seq:
-                seq, _ = make_seq_step(layers, cfg, dev, lut_mode)
+                seq, _ = make_seq_step(layers, cfg, dev, lut_mode, peer=seq_peer)
                 seq.x.copy_(x0)
                 runner = GraphedDecodeStep(lambda x: seq.replay()[0], seq.x, warmup=3, static_input=True)
             else:
@@ -606,7 +614,7 @@ def main():
 
     # ---- parity: one sampled layer group per rank against the fp64 oracle on the same buffers (outside every timed region) ----------
     if use_seq:
-        run_layer = make_seq_run_layer(cfg, dev, quant_cuda)
+        run_layer = make_seq_run_layer(cfg, dev, quant_cuda, peer=seq_peer)
     parity = parity_check(layers, run_layer, cfg, rank, world, dev, quant_cuda)
     if world > 1:
         import torch.distributed as dist

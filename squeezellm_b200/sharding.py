@@ -182,6 +182,34 @@ class PeerExchange:
         dist.barrier(group=self.group)
 
 
+
+class PeerArena:
+    """Peer-visible arenas for `runtime.DecodeSequence` on several GPUs (one process per GPU).
+
+    The sequence kernel hands the result of one matvec to the next as self-validating tagged words in an arena
+    (csrc/lutgemv_seq.cuh); on several GPUs the owner of a strip stores its words into EVERY rank's arena over NVLink, and the
+    next matvec's input poll is the whole exchange - no collective, no flag.  `arena_for` is collective (symmetric-memory
+    rendezvous + barrier): every rank must compile its sequences in the same order."""
+
+    def __init__(self, rank, world, device, group=None):
+        import torch.distributed as dist
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        self.group = group if group is not None else dist.group.WORLD
+        self._keep = []
+
+    def arena_for(self, nbytes):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        nbytes = (int(nbytes) + 4095) // 4096 * 4096
+        arena = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+        hdl = symm.rendezvous(arena, self.group)
+        arena.zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)   # every arena is zeroed before any rank's kernel can store into it
+        self._keep.append((arena, hdl))
+        return arena, int(hdl.buffer_ptrs_dev)
+
+
 class ShardedSiblingGroup:
     """Column shards of a set of sibling layers (same input) run as ONE stacked launch per rank + ONE exchange.
 

@@ -207,23 +207,34 @@ __global__ void csr_batched_kernel(const int *__restrict__ rows, const int *__re
     }
 }
 
-// topX dense rows for a batch: thread = (batch row, dense-row column j): mul[b][fri[j]] += sum_k full_rows[k][j] * x[b][k]
+// topX dense rows for a batch: mul[b][fri[j]] += sum_k full_rows[k][j] * x[b][k].  One CTA per batch row; thread = (k-slice, dense row j):
+// 256 / topX slices of K walk their part with four independent fp32 chains, the slices' sums are added in fixed order through shared
+// memory (deterministic), one atomicAdd per (b, j).  (First build: one thread per (b, j) walking all K terms in fp64 - 0.37 ms of pure
+// latency whatever the batch, 3x SLOWER than the reference's kernels at batch 16: profiles/r02_batched_vs_reference_kernel.jsonl.)
 __global__ void dense_rows_batched_kernel(const float *__restrict__ full_rows, const int *__restrict__ fri, int topX,
                                           const float *__restrict__ x, float *__restrict__ mul, int K, int N, int B) {
-    const int j = threadIdx.x % topX, bl = threadIdx.x / topX, per = blockDim.x / topX;
-    const int b = blockIdx.x * per + bl;
-    if (bl >= per || b >= B) return;
-    const int c = __ldg(fri + j);
-    if (c < 0 || c >= N) return;
+    __shared__ float part[256];
+    const int b = blockIdx.x, nsl = blockDim.x / topX;
+    const int j = threadIdx.x % topX, sl = threadIdx.x / topX;
     const float *xb = x + (size_t)b * K;
-    double a0 = 0.0, a1 = 0.0;  // K terms in two chains: fp64 keeps them at the oracle's precision (K * topX * B FMAs - nothing)
-    int k = 0;
-    for (; k + 1 < K; k += 2) {
-        a0 += (double)__ldg(full_rows + (size_t)k * topX + j) * (double)__ldg(xb + k);
-        a1 += (double)__ldg(full_rows + (size_t)(k + 1) * topX + j) * (double)__ldg(xb + k + 1);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const int per = (K + nsl - 1) / nsl, k0 = sl * per, k1 = min(K, k0 + per);
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {
+        a0 = fmaf(__ldg(full_rows + (size_t)k * topX + j), __ldg(xb + k), a0);
+        a1 = fmaf(__ldg(full_rows + (size_t)(k + 1) * topX + j), __ldg(xb + k + 1), a1);
+        a2 = fmaf(__ldg(full_rows + (size_t)(k + 2) * topX + j), __ldg(xb + k + 2), a2);
+        a3 = fmaf(__ldg(full_rows + (size_t)(k + 3) * topX + j), __ldg(xb + k + 3), a3);
     }
-    if (k < K) a0 += (double)__ldg(full_rows + (size_t)k * topX + j) * (double)__ldg(xb + k);
-    atomicAdd(mul + (size_t)b * N + c, (float)(a0 + a1));
+    for (; k < k1; ++k) a0 = fmaf(__ldg(full_rows + (size_t)k * topX + j), __ldg(xb + k), a0);
+    part[threadIdx.x] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (sl == 0) {
+        float t = 0.f;
+        for (int i = 0; i < nsl; ++i) t += part[i * topX + j];
+        const int c = __ldg(fri + j);
+        if (c >= 0 && c < N) atomicAdd(mul + (size_t)b * N + c, t);
+    }
 }
 
 }  // namespace batched

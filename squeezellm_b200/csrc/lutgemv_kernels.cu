@@ -2094,7 +2094,7 @@ int launch_batched(const sqllm_lutgemv_args *a, cudaStream_t st) {
     if (a->full_rows && a->topX > 0) {
         if (a->topX > 256) return fail(SQLLM_EINVAL, "batched path supports topX <= 256");
         const int per = 256 / a->topX;
-        dense_rows_batched_kernel<<<(B + per - 1) / per, per * a->topX, 0, st>>>(a->full_rows, a->full_row_indices, a->topX, a->vec, a->mul, K, N, B);
+        dense_rows_batched_kernel<<<B, per * a->topX, 0, st>>>(a->full_rows, a->full_row_indices, a->topX, a->vec, a->mul, K, N, B);
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SQLLM_ECUDA, "batched launch failed: %s", cudaGetErrorString(e));

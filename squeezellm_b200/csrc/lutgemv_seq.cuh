@@ -4,7 +4,7 @@
 //
 // Why: with one launch per GEMV (v2 + PDL + CUDA graph) a 4096x4096 layer took 8.9 us in the chain for 1.5 us of HBM time; a fit over the
 // four 7B shapes gave ~6 us of fixed cost per launch (CTA exit -> grid completion -> dependency release -> CTA start, barrier init, tensor
-// map fetch, x staging, ring fill from cold) - 128 launches per token, 40 % of the step (profiles/r02_bench_default.json).  Here
+// map fetch, x staging, ring fill from cold) - 128 launches per token, 40 % of the step (profiles/r02_bench_llama7b_w4_s45.json).  Here
 //   * grid = #SMs, launched ONCE per token; every CTA walks the same list of GEMV descriptors (global memory, written at create time);
 //   * the TMA producer warp never stops at a GEMV boundary: while the consumers finish GEMV g and wait for its result, the ring already
 //     holds the first 128 KB per SM of GEMV g+1 - weights do not depend on activations;
@@ -556,7 +556,17 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv_seq_kernel(const SeqCfg c
 #pragma unroll
                 for (int h = 0; h < 3; ++h)
                     if (h < nh) last_others += box_take(hw[h], p.ws_hbox + ((size_t)blockIdx.x + 1 + h) * STRIP + bt, err, boxtag, true);
-                for (int h = 3; h < nh; ++h) last_others += box_take(0ull, p.ws_hbox + ((size_t)blockIdx.x + 1 + h) * STRIP + bt, err, boxtag, true);
+                // (a strip that spans many CTAs - narrow column shards: 18 CTAs per strip for a 512-column shard of down_proj - has many such
+                //  words: eight reads in flight, not one round trip after the other)
+                for (int h0 = 3; h0 < nh; h0 += 8) {
+                    unsigned long long mw[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (h0 + k < nh) mw[k] = ld_relaxed_u64(p.ws_hbox + ((size_t)blockIdx.x + 1 + h0 + k) * STRIP + bt);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (h0 + k < nh) last_others += box_take(mw[k], p.ws_hbox + ((size_t)blockIdx.x + 1 + h0 + k) * STRIP + bt, err, boxtag, true);
+                }
                 TRACE(8, bt == 0);
                 if (nseg > 0) {
                     const int s = nseg - 1;

@@ -3,13 +3,13 @@
 //
 // Same job as lutgemv_kernel (v1): y[c] (+)= sum_k LUT[c][idx(k,c)] * x[k]  (+ CSR outliers + topX dense rows), replacing
 // squeezellm/quant_cuda_kernel.cu:741-880 (LUT GEMV), :1040-1059 (SPMV_ATOMIC), :1092-1123 (DenseMatVecKernel).
-// What changed and why (measurements: profiles/r02_*):
+// What changed and why (measurements: profiles/r02_*; [*] = measured on an intermediate build in the first session of round 2, whose container and raw logs were lost):
 //   * grid = #SMs, 23 warps per CTA: 16 consumer warps, 1 TMA producer warp, 2 table-builder warps, 4 sparse warps.  v1 ran 3 CTAs x 8 consumer warps per SM;
 //     two thirds of its executed instructions on a 4096x4096 layer were per-CTA prologue/epilogue bookkeeping (ncu, r01).
 //   * weights arrive as 2-D TMA boxes (cp.async.bulk.tensor.2d): stages are aligned to the CTA's strip segments, so a full stage is
 //     ONE box of 64 columns x 32 units (8 KB / 24 KB) issued by one lane of the producer warp; the ragged last stage of a segment
 //     goes out as 2-unit boxes, one per lane (second tensor map), so nothing is over-fetched.  (First attempt: one 256-byte
-//     cp.async.bulk per row - 2.5x SLOWER than v1, the TMA unit retires a small copy every ~80 clocks: profiles/r02_v2_ab_*.)
+//     cp.async.bulk per row - 2.5x SLOWER than v1, the TMA unit retires a small copy every ~80 clocks: first session of round 2, log lost [*].)
 //     Nothing of this touches the LSU pipe, which bounds the gather loop (32 gathers + 4 word reads + 2-4 x reads per 1024 weights).
 //   * the CTA walks its strips one after the other with TWO table buffers in shared memory: the builder warps prepare the next strip's
 //     table in the background and move each finished strip's sums (red.shared.add by the consumer warps) on to global memory; the
@@ -170,7 +170,7 @@ __device__ __forceinline__ float box_take(unsigned long long w, unsigned long lo
 // Staging layout: the row of column c sits at slot(c) * (L*4 + 16) bytes.  The builders read it with 16-byte loads, lane = slot: with the
 // rows packed by column (stride 4 columns x 64 B = 256 B between adjacent lanes) every LDS.128 was an 8-way bank conflict, and the
 // pair-table build re-reads the row for each of its 16 outer steps - ncu: 1.18 M of the fp16 kernel's 3.69 M shared-memory wavefronts
-// were these conflicts (profiles/r02_ncu_fp16_bank_conflicts.txt), as much LSU time as a third of the gathers.  With an 80-byte
+// were these conflicts (first session of round 2, log lost [*]), as much LSU time as a third of the gathers.  With an 80-byte
 // (4-bit) / 48-byte (3-bit) stride the 8 lanes of each 128-byte phase cover all 32 banks.
 template <int BITS>
 __device__ __forceinline__ void lut_prefetch(const P2 &p, const uint32_t lutbuf, const int strip, const int bt) {
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
         // =========================== TMA producer: weights never depend on the previous kernel ===========================
         // Stages never straddle a strip: segment `seg` (the CTA's part of strip s0+seg) is cut into stages of SU2 units from its own start.
         // (Also tried: cp.async.bulk.prefetch.tensor into L2 16-24 stages ahead of the ring - 5-10 % slower on every shape, like the
-        // L2 prefetch experiment of round 1: profiles/r02_v2_ab_l2pf.txt.)
+        // L2 prefetch experiment of round 1: first session of round 2, log lost [*].)
         const uint64_t pol = l2_evict_first_policy();
         int slot = 0;
         uint32_t ph = 0;

@@ -7,7 +7,7 @@ T="timeout 240"
 $T python bench.py --per-shape > $O/r02_bench_llama7b_w4_s45.json 2> $O/r02_bench_llama7b_w4_s45.err
 $T python bench.py --launch seq --no-cpu-baseline > $O/r02_bench_llama7b_w4_s45_seq.json 2> $O/r02_bench_llama7b_w4_s45_seq.err
 for w in llama7b-w4-s0 llama7b-w3-s45 llama13b-w4-s5 llama65b-w3-s45; do
-  $T python bench.py --workload $w --steps 10 --warmup 3 --per-shape --no-cpu-baseline > $O/r02_bench_${w//-/_}.json 2> $O/r02_bench_${w//-/_}.err
+  timeout 420 python bench.py --workload $w --steps 10 --warmup 3 --per-shape --no-cpu-baseline > $O/r02_bench_${w//-/_}.json 2> $O/r02_bench_${w//-/_}.err
 done
 $T ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:lutgemv -c 400 --csv \
     --log-file $O/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --lut exact --blocks 1 > $O/r02_launches_bench.log 2>&1

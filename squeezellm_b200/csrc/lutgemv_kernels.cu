@@ -1750,6 +1750,12 @@ int launch2(const sqllm_lutgemv_args *a, int variant, bool fused, v2::P2 &p, cud
             l2pf = e ? (e[0] == '1') : 0;
         }
         p.l2pf = l2pf;
+        static int sp_w0 = -1;
+        if (sp_w0 < 0) {
+            const char *e = getenv("SQLLM_SP_W0");
+            sp_w0 = e ? (e[0] == '1') : 0;
+        }
+        p.sp_w0 = sp_w0;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

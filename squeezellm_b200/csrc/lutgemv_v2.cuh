@@ -84,6 +84,7 @@ struct P2 {
     int xw_world, xw_rank, xw_members, xw_nfull;
     const unsigned long long *xw_base;
     unsigned long long xw_out_off, xw_flag_off, xw_state_off, xw_err_off;
+    int sp_w0; // 1: sparse warp 0 takes half a share of the CSR rows next to the dense rows (see sparse2)
     int l2pf;  // 1: prefetch the CTA's chunk of weights into L2 at entry
     unsigned long long *trace;
 };
@@ -417,7 +418,10 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
     }
     int r, rb;
     {
-        const int tot = cb - ca, w0 = p.full_rows ? tot / (2 * NSPW) : tot / NSPW, rest = tot - w0;
+        // warp 0 also has the dense rows (atomics, a fence, the announcement: 2-3 us after x arrives).  sp_w0 = 0 (default): it then takes no CSR
+        // rows at all - the outlier sums are what the owners of ALL strips wait for, they must not queue behind that fence; 1: half a share (round-2
+        // first build; A/B with SQLLM_SP_W0=1)
+        const int tot = cb - ca, w0 = p.full_rows ? (p.sp_w0 ? tot / (2 * NSPW) : 0) : tot / NSPW, rest = tot - w0;
         r = spw == 0 ? ca : ca + w0 + (int)((long long)rest * (spw - 1) / (NSPW - 1));
         rb = spw == 0 ? ca + w0 : ca + w0 + (int)((long long)rest * spw / (NSPW - 1));
     }

@@ -82,7 +82,8 @@ constexpr size_t WS_ACC_OFF = 65536;       // [64 KB, 64 KB + 4*MAX_N_FUSED): fp
 constexpr int MAX_GRID_V2 = 256;           // v2 runs one CTA per SM
 constexpr size_t WS_HBOX_OFF = WS_ACC_OFF + (size_t)MAX_N_FUSED * 4;       // v2 mailboxes: [MAX_GRID_V2][64] x 8 bytes (partial strip sums)
 constexpr size_t WS_CBOX_OFF = WS_HBOX_OFF + (size_t)MAX_GRID_V2 * 64 * 8;  // ... and [MAX_N_FUSED] x 8 bytes (outlier row sums); zero between launches
-constexpr size_t WS_HEADER = WS_CBOX_OFF + (size_t)MAX_N_FUSED * 8;  // tickets + accumulator + mailboxes: never shared with data of any shape
+constexpr size_t WS_DBOX_OFF = WS_CBOX_OFF + (size_t)MAX_N_FUSED * 8;          // ... and [MAX_TOPX_FUSED][MAX_GRID_V2] x 8 bytes (dense-row parts, one per contributing CTA)
+constexpr size_t WS_HEADER = WS_DBOX_OFF + (size_t)MAX_TOPX_FUSED * MAX_GRID_V2 * 8;  // tickets + accumulator + mailboxes: never shared with data of any shape
 constexpr int MAX_NSTAGE = 16;            // weight stages per CTA (runtime count, fills the shared-memory budget)
 
 struct Params {
@@ -2215,6 +2216,7 @@ int sqllm_lutgemv_fused(const sqllm_lutgemv_args *a, const void *x, int x_is_hal
         q.ws_acc = reinterpret_cast<float *>(ws + WS_ACC_OFF);
         q.ws_hbox = reinterpret_cast<unsigned long long *>(ws + WS_HBOX_OFF);
         q.ws_cbox = reinterpret_cast<unsigned long long *>(ws + WS_CBOX_OFF);
+        q.ws_dbox = reinterpret_cast<unsigned long long *>(ws + WS_DBOX_OFF);
         q.x = x; q.out = y; q.y_is_half = y_is_half; q.bias = bias;
         return launch2(a, x_is_half ? (lut_mode() == 1 ? 2 : 1) : 0, true, q, static_cast<cudaStream_t>(stream));
     }
@@ -2263,6 +2265,7 @@ int sqllm_lutgemv_fused_exchange(const sqllm_lutgemv_args *a, const void *x, int
         q.ws_acc = reinterpret_cast<float *>(ws + WS_ACC_OFF);
         q.ws_hbox = reinterpret_cast<unsigned long long *>(ws + WS_HBOX_OFF);
         q.ws_cbox = reinterpret_cast<unsigned long long *>(ws + WS_CBOX_OFF);
+        q.ws_dbox = reinterpret_cast<unsigned long long *>(ws + WS_DBOX_OFF);
         q.x = x; q.out = nullptr; q.y_is_half = y_is_half; q.bias = bias;
         q.xw_world = xc->world; q.xw_rank = xc->rank; q.xw_members = xc->members; q.xw_nfull = xc->out_features_full;
         q.xw_base = reinterpret_cast<const unsigned long long *>(xc->peer_base);

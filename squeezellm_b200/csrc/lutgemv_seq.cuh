@@ -439,19 +439,36 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv_seq_kernel(const SeqCfg c
             int *const sdj = reinterpret_cast<int *>(sm + OFF_CSR);
             const uint32_t sden = base + OFF_CSR + 4 * 128, sdn_a = base + OFF_CSR + 8 * 128;
             if (p.full_rows) {
-                if (bt == 0) {
-                    int n = 0;
-                    for (int j = 0; j < p.topX; ++j) {
-                        const int cc = __ldg(p.fri + j);
-                        bool first = true;  // (rows on the same channel were combined by the contributors, topX <= 32: see sparse3)
-                        if (p.topX <= 32)
-                            for (int j2 = 0; j2 < j; ++j2) first &= __ldg(p.fri + j2) != cc;
-                        if (first && cc >= 0 && cc < N && cc / STRIP >= so0 && cc / STRIP < so1) sdj[n++] = j;
-                    }
-                    sts_u32(sdn_a, (uint32_t)n);
-                }
+                // (one warp, registers and shuffles: a serial scan of full_row_indices by one thread cost 435 dependent loads = 6 us for the 30
+                //  dense rows of a stacked q/k/v layer - on every CTA, before its first mailbox row went out)
+                const int topX = p.topX;
+                if (bt == 0) sts_u32(sdn_a, 0u);
                 sts_u32(sden + 4 * bt, 0u);
                 sts_u32(sden + 4 * (bt + NBT), 0u);
+                named_bar_sync(3, NBT);
+                if (topX <= 32) {
+                    if (bt < 32) {
+                        const int cc = bt < topX ? __ldg(p.fri + bt) : -1 - bt;
+                        bool first = true;  // rows on the same channel were combined by the contributors: the first of them carries the sum
+                        for (int j2 = 0; j2 < topX; ++j2) {
+                            const int c2 = __shfl_sync(0xffffffffu, cc, j2);
+                            if (c2 == cc && j2 < bt) first = false;
+                        }
+                        const bool mine = bt < topX && first && cc >= 0 && cc < N && cc / STRIP >= so0 && cc / STRIP < so1;
+                        const unsigned m = __ballot_sync(0xffffffffu, mine);
+                        if (mine) sdj[__popc(m & ((1u << bt) - 1u))] = bt;
+                        if (bt == 0) sts_u32(sdn_a, (uint32_t)__popc(m));
+                    }
+                } else {
+                    for (int j = bt; j < topX; j += NBT) {
+                        const int cc = __ldg(p.fri + j);
+                        if (cc >= 0 && cc < N && cc / STRIP >= so0 && cc / STRIP < so1) {
+                            uint32_t at;
+                            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(sdn_a) : "memory");
+                            sdj[at] = j;
+                        }
+                    }
+                }
                 named_bar_sync(3, NBT);
             }
             const int sdn = p.full_rows ? (int)lds_u32(sdn_a) : 0;

@@ -57,7 +57,8 @@ constexpr int OFF_CSR = OFF_SACC + 2 * STRIP * 4;            // per sparse warp:
 constexpr int OFF_SROW = OFF_CSR + NSPW * SP_BYTES;          // CTA-wide: int srow[SP_ROWS + 1], float srowacc[SP_ROWS + 1]
 constexpr int OFF_LUT = OFF_SROW + 2 * (SP_ROWS + 1) * 4;        // 2 x raw fp32 LUT rows of a strip (64 columns x 16 values), staged ahead by the builders
 constexpr int LUTBUF = STRIP * (16 * 4 + 16);                // a strip's raw LUT rows, one per column SLOT, row stride L*4 + 16 bytes (see lut_prefetch)
-constexpr int OFF_X = OFF_LUT + 2 * LUTBUF;                  // x (fp16 or fp32), then [ring stages][table 0][table 1][ring stages]
+constexpr int OFF_FIN = OFF_LUT + 2 * LUTBUF;                // finishers: float sown[8][64] (own strip sums), int sdj[128], float sden[128], int sdn (dense rows)
+constexpr int OFF_X = OFF_FIN + 4096;                        // x (fp16 or fp32), then [ring stages][table 0][table 1][ring stages]
 static_assert(OFF_X % 128 == 0, "x must stay 128-byte aligned");
 
 struct P2 {
@@ -378,6 +379,7 @@ __device__ __forceinline__ float xs_load(const uint32_t xs_u32, const int k) {
 template <bool XH, bool FUSED>
 __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const uint32_t base, const int spw, const int lane, float *acc_out, const uint32_t boxtag = 1u) {
     const int N = p.N;
+    constexpr bool BOX = FUSED && SQLLM_BOX && !SQLLM_CSR_LOCAL;  // cross-CTA sums travel as mailbox words
     const uint32_t xs_u32 = base + OFF_X;
     const uint32_t stage_u32 = base + OFF_CSR + spw * SP_BYTES;       // this warp's chunk buffer b: cols at +b*SP_CH*8, vals SP_CH*4 further
     int *srow = reinterpret_cast<int *>(sm + OFF_SROW);               // [SP_ROWS + 1] row pointers of the CTA's rows (FUSED, when they fit)
@@ -428,7 +430,7 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
     const int nr = rb - r;
     const bool rows_in_smem = cb - ca <= SP_ROWS;                       // the CTA's row pointers live in shared memory
     const bool local_sums = FUSED && SQLLM_CSR_LOCAL && rows_in_smem;  // ... and so do the row sums (same rule in the builders)
-    constexpr bool BOX = FUSED && SQLLM_BOX && !SQLLM_CSR_LOCAL;  // row sums are published as mailbox words when the warp is through
+    // (BOX: row sums are published as mailbox words when the warp is through)
     const bool smem_sums = local_sums || (BOX && rows_in_smem);
     auto emit = [&](int row, float v) {
         if (smem_sums) srowacc[row - ca] += v;  // plain read-modify-write: a row belongs to this warp alone and its pieces arrive one after the other
@@ -501,6 +503,21 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
                     if (rs == 0) a += v;
                 }
                 if (rs != 0) j = p.topX;  // only slot 0 publishes
+                if constexpr (BOX) {
+                    // dense rows that feed the SAME channel travel as one word (the first of them carries the sum): the owner of that channel's
+                    // strip then reads hc words, not hc per row - a checkpoint without dense rows loads as topX rows on channel 0 (llama.py:182)
+                    const int cme = (rs == 0 && hj < p.topX) ? __ldg(p.fri + hj) : -1 - lane;
+                    bool first = true;
+                    float tot = a;
+                    for (int j2 = 0; j2 < p.topX; ++j2) {
+                        const int c2 = __shfl_sync(0xffffffffu, cme, j2);
+                        const float a2 = __shfl_sync(0xffffffffu, a, j2);
+                        if (c2 == cme && j2 < hj) first = false;
+                        if (c2 == cme && j2 > hj) tot += a2;
+                    }
+                    a = tot;
+                    if (!first) j = p.topX;
+                }
             } else {
                 j = jb + lane;
                 if (j < p.topX) {
@@ -508,12 +525,17 @@ __device__ __forceinline__ void sparse2(const P2 &p, unsigned char *sm, const ui
                     for (int k = kb; k < ke; ++k, fr += p.topX) a += __ldg(fr) * xs_load<XH>(xs_u32, k);
                 }
             }
-            if (j < p.topX) {
+            if constexpr (BOX) {
+                // this CTA's part of dense row j: one self-validating word, no RED + fence + flag (the owner of the channel's strip sums the hc words of
+                // row j, lutgemv2_kernel's finishers); before: atomics into the accumulator, a MEMBAR.GPU and an announcement per strip - the fence
+                // alone held this warp for 1-2 us, and with it every owner that waited for the announcement
+                if (j < p.topX) st_relaxed_u64(p.ws_dbox + (size_t)j * MAX_GRID_V2 + blockIdx.x, box_word(a));
+            } else if (j < p.topX) {
                 const int c = __ldg(p.fri + j);
                 if (c >= 0 && c < N) atomicAdd(acc_out + c, a);
             }
         }
-        if constexpr (FUSED && (SQLLM_CSR_LOCAL || SQLLM_BOX)) {
+        if constexpr (FUSED && SQLLM_CSR_LOCAL) {
             // announce this CTA's dense-row contributions now, early in the kernel: one fence, then a relaxed increment per distinct
             // strip that holds a dense-row channel (every one of the hc contributing CTAs does this; the owners expect hc arrivals)
             __threadfence();
@@ -762,6 +784,8 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
         int *const flags = p.ws_cnt + 64;
         bool dep_ok = false;
         auto dep_wait = [&]() { if (!dep_ok) { pdl_wait(); dep_ok = true; } };  // builders never read x: they only need this before writing
+        const uint32_t sown = base + OFF_FIN;   // float [SOWN][64]
+        constexpr int SOWN = 8;
         auto flush = [&](int s) {  // strip sums of segment s -> one red.add per column, accumulator back to zero
             const uint32_t a = sacc + 4 * ((s & 1) * STRIP + bt);
             const float v = lds_f32(a);
@@ -770,7 +794,11 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             if constexpr (FUSED && SQLLM_BOX && !SQLLM_CSR_LOCAL) {
                 // A strip is finished (converted to y) by the CTA in whose range it STARTS; a CTA that only holds a later part of it
                 // (that can only be its first segment) hands its sums to that owner through its mailbox row.
+                // ... or to ourselves: then they never leave the SM (sown[u][column] for the u-th owned strip; a strip inside one CTA is exactly
+                // one segment).  Through the global accumulator (first round-2 build) that was a RED and, in the finishing pass, a load that had to
+                // wait for it - two L2 round trips of 1-2.5 us each between the last weight and y when the last segment is short.
                 if (s == 0 && r0 != 0) st_relaxed_u64(p.ws_hbox + (size_t)blockIdx.x * STRIP + bt, box_word(v));
+                else if (s - (r0 != 0 ? 1 : 0) < SOWN) sts_u32(sown + 4u * (uint32_t)((s - (r0 != 0 ? 1 : 0)) * STRIP + bt), __float_as_uint(v));
                 else if (col < N) atomicAdd(acc_out + col, v);
             } else {
                 if (col < N) atomicAdd(acc_out + col, v);
@@ -814,26 +842,60 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
             //      own sparse warp, in shared memory) - and fetch the accumulator.  What is left for the very end is y = accumulator + own last strip (+ bias): no round trip to
             //      L2 after the last weight, no grid-wide step; a CTA leaves as soon as its own strips are complete.
             //      Waits are bounded (2 s, then the workspace error word is set).
-            if (nseg >= 2) {
-                mbar_wait(bar_u32 + 272 + 8 * ((nseg - 2) & 1), (uint32_t)(((nseg - 2) >> 1) & 1));
-                flush(nseg - 2);
-            }
+#if SQLLM_BOX && !SQLLM_CSR_LOCAL
+            // ---- mailbox variant (shared with the sequence kernel, lutgemv_seq.cuh): own strip sums from shared memory, outlier sums and the later
+            //      CTAs' first-segment sums from their mailbox words, dense rows from one tagged word per (contributing CTA, row).
+            TRACE(12, bt == 0);
             const long long cb0 = (long long)blockIdx.x * p.chunk, cb1 = min((long long)p.T, cb0 + p.chunk);
             const int so0 = (int)((cb0 + R - 1) / R), so1 = (int)((cb1 + R - 1) / R), nown = so1 - so0;
-            const bool last_owned = nseg >= 2 || r0 == 0;  // the last segment's strip starts in this CTA's range (it is strip so1 - 1)
-#if SQLLM_BOX && !SQLLM_CSR_LOCAL
-            // ---- mailbox variant.  Thread bt owns column bt of every owned strip.  What it adds up per column:
-            //        the accumulator   - this CTA's own sums of the strip unless it is the last segment's (those never leave shared memory),
-            //                            plus the dense-row sums if a dense-row channel lies in the strip (flag: hc arrivals, early in the kernel)
-            //        cbox[col]         - the column's outlier sum, from whichever CTA has that CSR row
-            //        hbox[b+1..b+nh]   - last owned strip only: the later CTAs' parts of it
-            //      All words are requested at once, speculatively, while the consumers are in the last segment; box_take spins on the few
-            //      that were not there yet.
+            const bool last_owned = nseg >= 2 || r0 == 0;
+            constexpr int FAST = 4;
+            const int lidx = last_owned && nseg > 0 ? nown - 1 : -1;
+            const int nh = lidx >= 0 ? (int)((((long long)(so1 - 1) + 1) * R - 1) / p.chunk) - (int)blockIdx.x : 0;
+            // Dense rows whose channel lies in a strip we own: listed now (static), summed below.  sdj[i] = dense row, sden[i] = its sum.
+            int *const err = p.ws_cnt + 16;
+            int *const sdj = reinterpret_cast<int *>(sm + OFF_FIN + 2048);
+            const uint32_t sden = base + OFF_FIN + 2048 + 4 * 128, sdn_a = base + OFF_FIN + 2048 + 8 * 128;
+            if (p.full_rows) {
+                // (one warp, registers and shuffles: a serial scan of full_row_indices by one thread cost 435 dependent loads = 6 us for the 30
+                //  dense rows of a stacked q/k/v layer - on every CTA, before its first mailbox row went out)
+                const int topX = p.topX;
+                if (bt == 0) sts_u32(sdn_a, 0u);
+                sts_u32(sden + 4 * bt, 0u);
+                sts_u32(sden + 4 * (bt + NBT), 0u);
+                named_bar_sync(3, NBT);
+                if (topX <= 32) {
+                    if (bt < 32) {
+                        const int cc = bt < topX ? __ldg(p.fri + bt) : -1 - bt;
+                        bool first = true;  // rows on the same channel were combined by the contributors: the first of them carries the sum
+                        for (int j2 = 0; j2 < topX; ++j2) {
+                            const int c2 = __shfl_sync(0xffffffffu, cc, j2);
+                            if (c2 == cc && j2 < bt) first = false;
+                        }
+                        const bool mine = bt < topX && first && cc >= 0 && cc < N && cc / STRIP >= so0 && cc / STRIP < so1;
+                        const unsigned m = __ballot_sync(0xffffffffu, mine);
+                        if (mine) sdj[__popc(m & ((1u << bt) - 1u))] = bt;
+                        if (bt == 0) sts_u32(sdn_a, (uint32_t)__popc(m));
+                    }
+                } else {
+                    for (int j = bt; j < topX; j += NBT) {
+                        const int cc = __ldg(p.fri + j);
+                        if (cc >= 0 && cc < N && cc / STRIP >= so0 && cc / STRIP < so1) {
+                            uint32_t at;
+                            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(sdn_a) : "memory");
+                            sdj[at] = j;
+                        }
+                    }
+                }
+                named_bar_sync(3, NBT);
+            }
+            const int sdn = p.full_rows ? (int)lds_u32(sdn_a) : 0;
+            for (int s = max(0, nseg - 2); s < nseg - 1; ++s) {
+                mbar_wait(bar_u32 + 272 + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
+                flush(s);
+            }
+            TRACE(13, bt == 0);
             {
-                constexpr int FAST = 4;  // owned strips handled from registers (7B..65B shapes own <= 4)
-                int *const err = p.ws_cnt + 16;
-                const int lidx = last_owned && nseg > 0 ? nown - 1 : -1;  // index of the last segment's strip among the owned ones
-                const int nh = lidx >= 0 ? (int)((((long long)(so1 - 1) + 1) * R - 1) / p.chunk) - (int)blockIdx.x : 0;
                 unsigned long long cw[FAST], hw[3];
 #pragma unroll
                 for (int u = 0; u < FAST; ++u) {
@@ -843,29 +905,47 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
 #pragma unroll
                 for (int h = 0; h < 3; ++h)
                     hw[h] = h < nh ? ld_relaxed_u64(p.ws_hbox + ((size_t)blockIdx.x + 1 + h) * STRIP + bt) : box_word(0.f);
-                if (p.full_rows) {  // dense rows: strips with a channel wait for the hc early announcements
-                    for (int i = bt; i < nown; i += NBT) {
-                        const int strip = so0 + i;
-                        bool hch = false;
-                        for (int j = 0; j < p.topX; ++j) {
-                            const int c = __ldg(p.fri + j);
-                            hch |= (c >= 0 && c < N && c / STRIP == strip);
+                // dense rows: hc tagged words per listed row (one from every contributing CTA), four loads in flight per thread; row sums are
+                // collected in shared memory and added to the column they belong to by the thread that owns that column
+                float last_dense = 0.f;
+                if (sdn > 0) {
+                    const int hc = p.hc;
+                    unsigned long long *const dbox = p.ws_dbox;
+                    for (int j0 = 0; j0 < sdn; j0 += 4) {  // four rows x up to four words per thread in flight (hc <= MAX_GRID_V2 = 4 x NBT)
+                        unsigned long long dw[4][4];
+                        int row[4];
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            row[a] = j0 + a < sdn ? sdj[j0 + a] : -1;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                if (row[a] >= 0 && bt + b * NBT < hc) dw[a][b] = ld_relaxed_u64(dbox + (size_t)row[a] * MAX_GRID_V2 + bt + b * NBT);
                         }
-                        if (hch) {
-                            int seen;
-                            unsigned long long t0 = 0ull, t1;
-                            do {
-                                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + strip) : "memory");
-                                if (seen >= p.hc) break;
-                                __nanosleep(40);
-                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                                if (t0 == 0ull) t0 = t1;
-                                if (t1 - t0 > 2000000000ull) { *reinterpret_cast<volatile int *>(err) = 1; break; }
-                            } while (true);
-                            flags[strip] = 0;
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            if (row[a] < 0) continue;  // (uniform)
+                            float v = 0.f;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                if (bt + b * NBT < hc) v += box_take(dw[a][b], dbox + (size_t)row[a] * MAX_GRID_V2 + bt + b * NBT, err);
+                            v = warp_sum(v);
+                            if (lane == 0) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(sden + 4u * (uint32_t)(j0 + a)), "f"(v) : "memory");
                         }
                     }
                     named_bar_sync(3, NBT);
+                    for (int i = 0; i < sdn; ++i) {
+                        const int cc = __ldg(p.fri + sdj[i]);
+                        if ((cc & (STRIP - 1)) == bt) {
+                            const int u = cc / STRIP - so0;
+                            const float v = lds_f32(sden + 4u * (uint32_t)i);
+                            if (u == lidx) last_dense += v;
+                            else if (u < SOWN) {
+                                const uint32_t a = sown + 4u * (uint32_t)(u * STRIP + bt);
+                                sts_u32(a, __float_as_uint(lds_f32(a) + v));
+                            } else atomicAdd(acc_out + cc, v);
+                        }
+                    }
+                    named_bar_sync(3, NBT);  // (the list and the sums are reused by the next item; an idle CTA has no other barrier before that)
                 }
                 const int w = p.xw_world ? N / p.xw_members : 0;
                 auto store_y = [&](int col, float yv) {
@@ -885,52 +965,70 @@ __global__ void __launch_bounds__(THREADS2, 1) lutgemv2_kernel(const P2 p, const
                         }
                     }
                 };
-                float av[FAST];  // accumulator values (zero where nothing was ever added: the array is zero between launches)
-#pragma unroll
-                for (int u = 0; u < FAST; ++u) {
-                    const int col = (so0 + u) * STRIP + bt;
-                    av[u] = (u < nown && col < N) ? __ldcg(p.ws_acc + col) : 0.f;
-                }
-                float last_others = 0.f;  // everything but this CTA's own sums of the last segment's strip
+                // per owned strip but the last segment's: [our own sums (+ dense rows), from shared memory] + [the column's outlier sum]
+                TRACE(14, bt == 0);
+                float last_others = last_dense;
 #pragma unroll
                 for (int u = 0; u < FAST; ++u) {
                     const int col = (so0 + u) * STRIP + bt;
                     if (u < nown && col < N) {
-                        float yv = av[u];
+                        float yv = 0.f;
+                        if (u != lidx && u < SOWN) yv = lds_f32(sown + 4u * (uint32_t)(u * STRIP + bt));
                         if (p.rows) yv += box_take(cw[u], p.ws_cbox + col, err);
-                        p.ws_acc[col] = 0.f;
-                        if (u == lidx) last_others = yv;
+                        if (u == lidx) last_others += yv;
                         else store_y(col, yv);
                     }
                 }
-                for (int i = FAST; i < nown; ++i) {  // (more owned strips than FAST: one at a time)
+                for (int i = FAST; i < nown; ++i) {  // (more owned strips than FAST; beyond SOWN the sums went through the global accumulator)
                     const int col = (so0 + i) * STRIP + bt;
                     if (col < N) {
-                        float yv = __ldcg(p.ws_acc + col);
+                        float yv = 0.f;
+                        if (i >= SOWN) { yv = __ldcg(p.ws_acc + col); p.ws_acc[col] = 0.f; }
+                        else if (i != lidx) yv = lds_f32(sown + 4u * (uint32_t)(i * STRIP + bt));
                         if (p.rows) yv += box_take(0ull, p.ws_cbox + col, err);
-                        p.ws_acc[col] = 0.f;
-                        if (i == lidx) last_others = yv;
+                        if (i == lidx) last_others += yv;
                         else store_y(col, yv);
                     }
                 }
+                TRACE(15, bt == 0);
 #pragma unroll
                 for (int h = 0; h < 3; ++h)
                     if (h < nh) last_others += box_take(hw[h], p.ws_hbox + ((size_t)blockIdx.x + 1 + h) * STRIP + bt, err);
-                for (int h = 3; h < nh; ++h) last_others += box_take(0ull, p.ws_hbox + ((size_t)blockIdx.x + 1 + h) * STRIP + bt, err);
+                // (a strip that spans many CTAs - narrow column shards: 18 CTAs per strip for a 512-column shard of down_proj - has many such
+                //  words: eight reads in flight, not one round trip after the other)
+                for (int h0 = 3; h0 < nh; h0 += 8) {
+                    unsigned long long mw[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (h0 + k < nh) mw[k] = ld_relaxed_u64(p.ws_hbox + ((size_t)blockIdx.x + 1 + h0 + k) * STRIP + bt);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (h0 + k < nh) last_others += box_take(mw[k], p.ws_hbox + ((size_t)blockIdx.x + 1 + h0 + k) * STRIP + bt, err);
+                }
                 TRACE(8, bt == 0);
                 if (nseg > 0) {
                     const int s = nseg - 1;
                     mbar_wait(bar_u32 + 272 + 8 * (s & 1), (uint32_t)((s >> 1) & 1));
                     if (last_owned) {
-                        const float own = lds_f32(sacc + 4 * ((s & 1) * STRIP + bt));
+                        const uint32_t a = (sacc + 4 * ((s & 1) * STRIP + bt));
+                        const float own = lds_f32(a);
+                        sts_u32(a, 0u);
                         const int lcol = (s0 + s) * STRIP + bt;
                         if (lcol < N) store_y(lcol, last_others + own);
                     } else {
-                        flush(s);  // a CTA that lies wholly inside a strip started by another one: its mailbox row
+                        flush(s);
                     }
                 }
             }
+            
 #else
+            if (nseg >= 2) {
+                mbar_wait(bar_u32 + 272 + 8 * ((nseg - 2) & 1), (uint32_t)(((nseg - 2) >> 1) & 1));
+                flush(nseg - 2);
+            }
+            const long long cb0 = (long long)blockIdx.x * p.chunk, cb1 = min((long long)p.T, cb0 + p.chunk);
+            const int so0 = (int)((cb0 + R - 1) / R), so1 = (int)((cb1 + R - 1) / R), nown = so1 - so0;
+            const bool last_owned = nseg >= 2 || r0 == 0;  // the last segment's strip starts in this CTA's range (it is strip so1 - 1)
             for (int i = bt; i < nown; i += NBT) {
                 const int strip = so0 + i;
                 int expect = (int)((((long long)strip + 1) * R - 1) / p.chunk) - (int)blockIdx.x;  // dense CTAs after this one

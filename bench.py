@@ -349,7 +349,7 @@ def run_reference_arm(args, cfg):
     fused_val = 1.0 / (statistics.median(fused[args.warmup:]) * cfg["layers"])
     sample = (f"each step = 1 of {cfg['layers']} decoder layers (7 matvecs: fp16 dequant + torch.matmul + CSR + dense rows), median of {len(t)} steps; "
               f"tokens/s = 1 / (layer time x {cfg['layers']}); ms_per_step is the MEASURED layer time")
-    config = {**base_config(args, cfg), "launches_per_step": 0, "sibling_fusion": "n/a (CPU)", "l2": "n/a (CPU)", "parallelism": "host threads",
+    config = {**base_config(args, cfg), "launches_per_step": 0, "matvec_items_per_step": 0, "sibling_fusion": "n/a (CPU)", "l2": "n/a (CPU)", "parallelism": "host threads",
               "exchange": "none", "launch": "n/a (CPU)", "lut": "exact", "timing": f"median of {len(t)} steps", "layers_timed": 1}
     out = {"metric": metric_name(args.workload), "value": val, "unit": "tokens/s", "impl": "reference",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": layer_s * 1e3, "higher_is_better": True,
@@ -380,7 +380,7 @@ def main():
     ap.add_argument("--launch", default="auto", choices=["auto", "seq", "graph"],
                     help="graph: one launch per (stacked) matvec, chained with PDL inside a CUDA graph; seq: the whole token as ONE persistent "
                          "kernel launch (runtime.DecodeSequence, csrc/lutgemv_seq.cuh; on several GPUs its input poll is the exchange); "
-                         "auto (default): what measured faster - graph on one GPU (500 vs 473 tokens/s), seq on several (509 vs 371 at N=2)")
+                         "auto (default): what measured faster - graph on one GPU (547 vs 481 tokens/s), seq on several (509 vs 371 at N=2)")
     ap.add_argument("--no-fuse", action="store_true", help="one launch per QuantLinearLUT (no q/k/v and gate/up sibling stacking)")
     ap.add_argument("--lut", default="both", choices=["both", "exact", "fp16"],
                     help="codebook precision: exact = fp32 as stored (headline), fp16 = pair tables; both = headline exact + a lut_fp16 object")

@@ -228,7 +228,8 @@ def make_seq_run_layer(cfg, dev, quant_cuda, peer=None):
         seq.x.copy_(x)
         outs = [o.clone() for o in seq.replay()]
         torch.cuda.synchronize()
-        assert not seq.error(), "a bounded in-kernel wait of the sequence gave up"
+        if seq.error():
+            print("[bench] parity_check: a bounded in-kernel wait of the sequence gave up; its vectors are incomplete", file=sys.stderr)
         ys, xs = outs[:len(rec)], iter(outs[len(rec):])
         return [(r[0], x if r[1].item < 0 else next(xs), y) for r, y in zip(rec, ys)]
     return run_layer
@@ -513,6 +514,12 @@ def main():
         for _ in range(args.warmup):
             one_step()
         barrier()
+        warm_timeout = False
+        if seq is not None and seq.error():  # start-up skew between ranks (> 2 s) during warm-up: note it, clear it, go on aligned
+            warm_timeout = True
+            seq.reset_error()
+            print(f"[bench] rank {rank}: a bounded in-kernel wait timed out during warm-up (start-up skew); cleared", file=sys.stderr)
+            barrier()
         if sample_clocks and rank == 0:
             sampler.start()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.blocks + 1)]
@@ -552,11 +559,14 @@ def main():
             blocks, e2e_ms = t.tolist()[:-1], t.tolist()[-1]
         ms = statistics.median(blocks)
         quant_cuda.set_lut_mode("exact")
+        seq_timeout = False
         if seq is not None:
-            assert not seq.error(), "a bounded in-kernel wait of the sequence kernel gave up during the timed run: the numbers are void"
+            seq_timeout = bool(seq.error())  # a bounded in-kernel wait gave up during the timed run: the numbers of this run are void
+            if seq_timeout:
+                print(f"[bench] rank {rank}: the sequence kernel's error word is set after the timed region - THIS RUN'S NUMBERS ARE VOID", file=sys.stderr)
             del runner, seq
             torch.cuda.empty_cache()
-        return {"ms_step": ms / args.steps, "e2e_ms_step": e2e_ms / args.steps, "blocks_ms": [round(b, 4) for b in blocks],
+        return {"seq_timeout": seq_timeout, "warm_timeout": warm_timeout, "ms_step": ms / args.steps, "e2e_ms_step": e2e_ms / args.steps, "blocks_ms": [round(b, 4) for b in blocks],
                 "graphed": graphed, "clocks": clocks}
 
     def per_shape(lut_mode):
@@ -623,6 +633,11 @@ def main():
         parity["max_rel_err"], parity["fp16_max_norm_err"] = t.tolist()
         parity["ranks"] = world
 
+    if main_run.get("seq_timeout") or (extra_run or {}).get("seq_timeout"):
+        parity["sequence_wait_timeout_in_timed_region"] = True
+        parity["ok"] = False
+    if main_run.get("warm_timeout"):
+        parity["sequence_wait_timeout_during_warmup_cleared"] = True
     if peer_used is not None and peer_used.error():  # a bounded in-kernel wait gave up: the numbers of this run are not valid
         exchange_used += " - ERROR: a peer wait timed out during this run"
         print(f"[bench] rank {rank}: exchange error word is set", file=sys.stderr)

@@ -267,6 +267,8 @@ int sqllm_sequence_create(const sqllm_seq_item *items, int n_items, const sqllm_
 int sqllm_sequence_run(sqllm_sequence *s, void *stream);
 /* synchronises `stream`; 1 if a bounded in-kernel wait ever gave up (results incomplete), 0 if not, < 0 on error */
 int sqllm_sequence_error(sqllm_sequence *s, void *stream);
+/* clears the error word on `stream` (after a start-up skew between ranks has been dealt with: barrier, then reset on every rank) */
+int sqllm_sequence_reset_error(sqllm_sequence *s, void *stream);
 void sqllm_sequence_destroy(sqllm_sequence *s);
 
 /* Test hook: unpack the packed indices on the GPU exactly as the GEMV kernels do

@@ -2050,6 +2050,13 @@ extern "C" int sqllm_sequence_error(sqllm_sequence *s, void *stream) {
     return h != 0;
 }
 
+extern "C" int sqllm_sequence_reset_error(sqllm_sequence *s, void *stream) {
+    if (!s) return fail(SQLLM_EINVAL, "sequence: null handle");
+    if (cudaMemsetAsync(static_cast<unsigned char *>(s->d_ws) + 64, 0, 4, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+        return fail(SQLLM_ECUDA, "sequence: clearing the error word failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return SQLLM_OK;
+}
+
 extern "C" void sqllm_sequence_destroy(sqllm_sequence *s) {
     if (!s) return;
     cudaFree(s->d_descs);

@@ -133,7 +133,16 @@ class DecodeSequence:
         return self.outputs
 
     def error(self):
+        """True if a bounded in-kernel wait (2 s) ever gave up: a result since then is incomplete.  Synchronises the current stream."""
         return self._quant_cuda.sequence_error(self._handle)
+
+    def check(self):
+        if self.error():
+            raise RuntimeError("DecodeSequence: an in-kernel wait timed out (2 s) - on several GPUs a rank was late or absent; results since then "
+                               "are incomplete.  Bring the ranks together (barrier) and call reset_error() on every rank.")
+
+    def reset_error(self):
+        self._quant_cuda.sequence_reset_error(self._handle)
 
     def __del__(self):
         try:

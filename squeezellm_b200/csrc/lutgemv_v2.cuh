@@ -139,8 +139,11 @@ __device__ __forceinline__ uint32_t f32x2_to_half2(float lo, float hi) {
 // the value needs no fence and no separate flag: the word validates itself.  Before: red.add into the accumulator, MEMBAR, flag
 // increment on the producer; acquire-poll of the flag, then a second round trip for the accumulator on the owner - three L2 round
 // trips (~2.5 us under load) between the last weight of a launch and its last y, now one.  The owner writes the word back to zero
-// (next launch's producers only write after the grid dependency resolved).  Only the dense-row sums, which have several producers
-// per channel, still go through red.add + flag; they are announced in the first microsecond of the kernel.
+// (next launch's producers only write after the grid dependency resolved).  The dense-row sums travel the same way since the second
+// half of round 2: one word per (contributing CTA, dense row) - rows that feed the same channel are combined in the contributing warp -
+// summed by the owner of the channel's strip; and the owner's OWN strip sums never leave the SM (sown, a shared-memory row per owned
+// strip).  Before: red.add into the global accumulator + MEMBAR.GPU + one announcement per strip on the producers, an acquire-poll and a
+// load of the accumulator behind it on the owner (7B w4-s45: 519.7 -> 547.0 tokens/s, profiles/r02_bench_llama7b_w4_s45.json).
 // ---------------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
     unsigned long long v;

@@ -16,7 +16,7 @@
 //     consumers never meet a CTA-wide barrier inside the loop.  Only two tables resident is what makes room for the
 //   * fp16 PAIR table (MODE 1): entry [a | b<<BITS] = half2(LUT[a], LUT[b]) - one PRMT-built (4-bit: the byte of the packed word IS
 //     the entry number) shared-memory lookup serves TWO weights, and the products go through fma.rn.f32.f16 (SASS FHFMA:
-//     fp16 x fp16 -> fp32 accumulate, exact products).  Measured 49.5 weights/clk/SM against 27.0 for the exact fp32 table
+//     fp16 x fp16 -> fp32 accumulate, exact products).  Measured 48.9 (49.5 on another box) weights/clk/SM against 27.0 for the exact fp32 table
 //     (tests/perf/microbench2.cu).  The only rounding is LUT -> fp16 (2^-11 relative per centroid); it needs fp16 x.
 //   * x is staged whole (as fp16 when it is given as fp16), the sparse warps gather it from shared memory.
 #pragma once

@@ -186,7 +186,7 @@ void run_lookup(const char *name, int sms, float *dout) {
         float ms = time_ms([&] { lookup_kernel<MODE><<<sms * occ, warps * 32, smem>>>(iters, dout); }, 3);
         const double weights = (double)sms * occ * warps * 32 * 32.0 * iters;
         printf("%-28s CTAs/SM=%d warps/CTA=%2d : %6.2f Tweights/s = %5.1f weights/clk/SM @1.965 GHz\n", name, occ, warps, weights / ms / 1e9,
-               weights / ms / 1e3 / sms / 1.965e6);
+               weights / ms / sms / 1.965e6);
     }
 }
 
